@@ -1,0 +1,697 @@
+// C-ABI of libdiffphar_b200.so (include/diffphar_b200.h): handle, weight packing, batch plan,
+// and the orchestration of one denoiser evaluation / one reverse-diffusion run.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+// --------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void dp_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* dp_last_error(void) { return g_err; }
+extern "C" int dp_abi_version(void) { return DP_ABI_VERSION; }
+
+extern "C" int dp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+// --------------------------------------------------------------------------------------
+// profiling spans (eager mode only)
+// --------------------------------------------------------------------------------------
+void prof_begin(dp_handle* h, int which, cudaStream_t st)
+{
+    if (!h->profile || h->spans.size() > 60000) return;
+    dp_handle::Span s; s.which = which;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, st);
+    h->spans.push_back(s);
+}
+
+void prof_end(dp_handle* h, cudaStream_t st)
+{
+    if (!h->profile || h->spans.empty()) return;
+    cudaEventRecord(h->spans.back().b, st);
+}
+
+// --------------------------------------------------------------------------------------
+// allocation helpers
+// --------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(std::vector<void*>& bag, T** out, size_t count)
+{
+    void* p = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    DP_CUDA(cudaMalloc(&p, bytes));
+    bag.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return DP_OK;
+}
+
+static int upload(std::vector<void*>& bag, float** out, const std::vector<float>& v)
+{
+    int rc = dev_alloc(bag, out, v.size());
+    if (rc) return rc;
+    if (!v.empty()) DP_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return DP_OK;
+}
+
+static void free_bag(std::vector<void*>& bag)
+{
+    for (void* p : bag) cudaFree(p);
+    bag.clear();
+}
+
+// --------------------------------------------------------------------------------------
+// create / destroy
+// --------------------------------------------------------------------------------------
+extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
+{
+    DP_CHECK(cfg && out, DP_ERR_INVALID, "dp_create: null argument");
+    DP_CHECK(cfg->hidden_nf == H, DP_ERR_INVALID, "hidden_nf must be %d (got %d): tiles are compile-time", H, cfg->hidden_nf);
+    DP_CHECK(cfg->n_dims == 3, DP_ERR_INVALID, "n_dims must be 3");
+    DP_CHECK(cfg->phar_nf > 0 && cfg->phar_nf <= 64 && cfg->residue_nf > 0 && cfg->residue_nf <= 64,
+             DP_ERR_INVALID, "phar_nf/residue_nf must be in [1,64]");
+    DP_CHECK(cfg->joint_nf > 0 && cfg->joint_nf <= 64, DP_ERR_INVALID, "joint_nf must be in [1,64]");
+    DP_CHECK(cfg->n_layers > 0 && cfg->inv_sublayers > 0, DP_ERR_INVALID, "n_layers/inv_sublayers must be positive");
+    DP_CHECK(cfg->precision >= DP_FP32 && cfg->precision <= DP_F16, DP_ERR_INVALID, "unknown precision %d", cfg->precision);
+    int n = 0;
+    DP_CUDA(cudaGetDeviceCount(&n));
+    DP_CHECK(device >= 0 && device < n, DP_ERR_INVALID, "device %d out of range (%d visible)", device, n);
+    int major = 0;
+    DP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    DP_CHECK(major == 10, DP_ERR_INVALID, "device %d is sm_%dx; this library is built for sm_100a only", device, major);
+    DP_CUDA(cudaSetDevice(device));
+    dp_handle* h = new dp_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->precision = cfg->precision;
+    DP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    int rc = egnn_f32_init();
+    if (!rc) rc = tc_init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return DP_OK;
+}
+
+static void free_plan(dp_handle* h)
+{
+    if (h->plan.step_graph) { cudaGraphExecDestroy(h->plan.step_graph); }
+    free_bag(h->plan.allocations);
+    h->plan = Plan();
+    h->has_plan = false;
+}
+
+extern "C" int dp_destroy(dp_handle* h)
+{
+    if (!h) return DP_OK;
+    cudaSetDevice(h->device);
+    free_plan(h);
+    free_bag(h->w.allocations);
+    tc_free_weights(h);
+    for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    delete h;
+    return DP_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// weights
+// --------------------------------------------------------------------------------------
+static int64_t weight_count_of(const dp_config& c)
+{
+    const int64_t P = c.phar_nf, R = c.residue_nf, J = c.joint_nf, D = J + (c.condition_time ? 1 : 0);
+    auto lin = [](int64_t o, int64_t i, bool b = true) { return o * i + (b ? o : 0); };
+    int64_t n = lin(2 * P, P) + lin(J, 2 * P) + lin(2 * P, J) + lin(P, 2 * P) + lin(2 * R, R) + lin(J, 2 * R) +
+                lin(2 * R, J) + lin(R, 2 * R) + lin(H, D) + lin(D, H);
+    const int64_t gcl = lin(H, 2 * H + 2) + lin(H, H) + lin(H, 2 * H) + lin(H, H) + (c.attention ? lin(1, H) : 0);
+    const int64_t crd = lin(H, 2 * H + 2) + lin(H, H) + lin(1, H, false);
+    n += (int64_t)c.n_layers * (c.inv_sublayers * gcl + crd);
+    return n;
+}
+
+extern "C" int64_t dp_weight_count(const dp_handle* h) { return h ? weight_count_of(h->cfg) : 0; }
+
+namespace {
+struct BlobReader {
+    const float* p;
+    const float* take(int64_t n) { const float* r = p; p += n; return r; }
+};
+
+// [out][in] row-major + bias  ->  transposed device linear
+int make_linear(std::vector<void*>& bag, DevLinear& L, const float* w, const float* b, int out, int in)
+{
+    std::vector<float> t((size_t)in * out);
+    for (int o = 0; o < out; ++o)
+        for (int k = 0; k < in; ++k) t[(size_t)k * out + o] = w[(size_t)o * in + k];
+    L.in = in; L.out = out;
+    int rc = upload(bag, &L.wt, t);
+    if (rc) return rc;
+    if (b) {
+        std::vector<float> bv(b, b + out);
+        rc = upload(bag, &L.b, bv);
+    }
+    return rc;
+}
+
+struct HostFirstLayer { const float* w; const float* b; };   // an [H][2H+2] first edge/coord layer
+}  // namespace
+
+extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
+{
+    DP_CHECK(h && blob, DP_ERR_INVALID, "dp_set_weights: null argument");
+    const dp_config& c = h->cfg;
+    DP_CHECK(n_floats == weight_count_of(c), DP_ERR_INVALID, "weight blob has %lld floats, expected %lld",
+             (long long)n_floats, (long long)weight_count_of(c));
+    DP_CUDA(cudaSetDevice(h->device));
+    free_bag(h->w.allocations);
+    h->w = DeviceWeights();
+    DeviceWeights& W = h->w;
+    auto& bag = W.allocations;
+    const int P = c.phar_nf, R = c.residue_nf, J = c.joint_nf, D = J + (c.condition_time ? 1 : 0);
+    BlobReader rd{blob};
+    int rc = 0;
+    auto lin = [&](DevLinear& L, int out, int in) {
+        const float* w = rd.take((int64_t)out * in);
+        const float* b = rd.take(out);
+        return make_linear(bag, L, w, b, out, in);
+    };
+    if ((rc = lin(W.phar_enc0, 2 * P, P))) return rc;
+    if ((rc = lin(W.phar_enc2, J, 2 * P))) return rc;
+    if ((rc = lin(W.phar_dec0, 2 * P, J))) return rc;
+    if ((rc = lin(W.phar_dec2, P, 2 * P))) return rc;
+    if ((rc = lin(W.res_enc0, 2 * R, R))) return rc;
+    if ((rc = lin(W.res_enc2, J, 2 * R))) return rc;
+    if ((rc = lin(W.res_dec0, 2 * R, J))) return rc;
+    if ((rc = lin(W.res_dec2, R, 2 * R))) return rc;
+    if ((rc = lin(W.emb, H, D))) return rc;
+    if ((rc = lin(W.emb_out, D, H))) return rc;
+
+    const int S = c.inv_sublayers, G = c.n_layers * S;
+    W.gcl.resize(G);
+    W.coord.resize(c.n_layers);
+    std::vector<HostFirstLayer> gcl_first(G), coord_first(c.n_layers);
+    const int K1 = 2 * H + 2;
+    auto scal_cols = [&](const float* w, float** wr, float** wd) {
+        std::vector<float> r(H), d(H);
+        for (int o = 0; o < H; ++o) { r[o] = w[(size_t)o * K1 + 2 * H]; d[o] = w[(size_t)o * K1 + 2 * H + 1]; }
+        int e = upload(bag, wr, r);
+        return e ? e : upload(bag, wd, d);
+    };
+    for (int b = 0; b < c.n_layers; ++b) {
+        for (int g = 0; g < S; ++g) {
+            GclWeights& L = W.gcl[b * S + g];
+            gcl_first[b * S + g].w = rd.take((int64_t)H * K1);
+            gcl_first[b * S + g].b = rd.take(H);
+            if ((rc = scal_cols(gcl_first[b * S + g].w, &L.wr, &L.wd))) return rc;
+            if ((rc = lin(L.e2, H, H))) return rc;
+            if ((rc = lin(L.n0, H, 2 * H))) return rc;
+            if ((rc = lin(L.n2, H, H))) return rc;
+            if (c.attention) {
+                const float* wa = rd.take(H);
+                const float* ba = rd.take(1);
+                std::vector<float> v(wa, wa + H);
+                if ((rc = upload(bag, &L.wa, v))) return rc;
+                L.ba = ba[0];
+            }
+        }
+        CoordWeights& Cw = W.coord[b];
+        coord_first[b].w = rd.take((int64_t)H * K1);
+        coord_first[b].b = rd.take(H);
+        if ((rc = scal_cols(coord_first[b].w, &Cw.wr, &Cw.wd))) return rc;
+        if ((rc = lin(Cw.c2, H, H))) return rc;
+        const float* w4 = rd.take(H);
+        std::vector<float> v(w4, w4 + H);
+        if ((rc = upload(bag, &Cw.w4, v))) return rc;
+    }
+    DP_CHECK(rd.p - blob == n_floats, DP_ERR_INVALID, "internal: blob walk consumed %lld of %lld floats",
+             (long long)(rd.p - blob), (long long)n_floats);
+
+    // Projection sets: h version v (v = 0 after the embedding, v = i+1 after GCL i) feeds the first
+    // layers of its consumers as ONE per-node GEMM with (row-part | col-part) outputs per consumer.
+    W.proj.resize(G + 1);
+    for (int v = 0; v <= G; ++v) {
+        std::vector<HostFirstLayer> cons;
+        ProjSet& ps = W.proj[v];
+        if (v > 0 && v % S == 0) { ps.off_coord = (int)cons.size() * 2 * H; cons.push_back(coord_first[v / S - 1]); }
+        if (v < G) { ps.off_gcl = (int)cons.size() * 2 * H; cons.push_back(gcl_first[v]); }
+        const int n_out = (int)cons.size() * 2 * H;
+        ps.lin.in = H; ps.lin.out = n_out;
+        if (n_out == 0) continue;
+        std::vector<float> wt((size_t)H * n_out), bias(n_out, 0.f);
+        for (size_t ci = 0; ci < cons.size(); ++ci) {
+            const int off = (int)ci * 2 * H;
+            for (int o = 0; o < H; ++o) {
+                bias[off + o] = cons[ci].b[o];                       // bias rides on the row part
+                for (int k = 0; k < H; ++k) {
+                    wt[(size_t)k * n_out + off + o] = cons[ci].w[(size_t)o * K1 + k];           // acts on h[row]
+                    wt[(size_t)k * n_out + off + H + o] = cons[ci].w[(size_t)o * K1 + H + k];   // acts on h[col]
+                }
+            }
+        }
+        if ((rc = upload(bag, &ps.lin.wt, wt))) return rc;
+        if ((rc = upload(bag, &ps.lin.b, bias))) return rc;
+    }
+    if ((rc = tc_prepare_weights(h, blob))) return rc;
+    h->has_weights = true;
+    if (h->plan.step_graph) { cudaGraphExecDestroy(h->plan.step_graph); h->plan.step_graph = nullptr; }
+    return DP_OK;
+}
+
+extern "C" int dp_set_precision(dp_handle* h, int precision)
+{
+    DP_CHECK(h, DP_ERR_INVALID, "null handle");
+    DP_CHECK(precision >= DP_FP32 && precision <= DP_F16, DP_ERR_INVALID, "unknown precision %d", precision);
+    h->precision = precision;
+    return DP_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// plan
+// --------------------------------------------------------------------------------------
+extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, const int32_t* res_counts, int64_t edge_capacity)
+{
+    DP_CHECK(h && phar_counts && res_counts, DP_ERR_INVALID, "dp_plan: null argument");
+    DP_CHECK(B > 0, DP_ERR_INVALID, "dp_plan: n_samples must be positive");
+    DP_CUDA(cudaSetDevice(h->device));
+    DP_CUDA(cudaDeviceSynchronize());
+    free_plan(h);
+    Plan& p = h->plan;
+    const dp_config& c = h->cfg;
+    std::vector<int> poff(B + 1, 0), roff(B + 1, 0);
+    double pairs = 0;
+    for (int b = 0; b < B; ++b) {
+        DP_CHECK(phar_counts[b] >= 0 && res_counts[b] >= 0, DP_ERR_INVALID, "negative node count in sample %d", b);
+        poff[b + 1] = poff[b] + phar_counts[b];
+        roff[b + 1] = roff[b] + res_counts[b];
+        const double nb = (double)phar_counts[b] + res_counts[b];
+        pairs += nb * nb;
+        if (phar_counts[b] > p.max_phar) p.max_phar = phar_counts[b];
+    }
+    p.B = B; p.Np = poff[B]; p.Nr = roff[B]; p.N = p.Np + p.Nr;
+    DP_CHECK(p.N > 0, DP_ERR_INVALID, "dp_plan: empty batch");
+    int64_t ecap = edge_capacity;
+    if (ecap <= 0) {
+        const double guess = (double)p.N * 128.0 > 65536.0 ? (double)p.N * 128.0 : 65536.0;
+        ecap = (int64_t)((c.edge_cutoff < 0.f || pairs < guess) ? pairs : guess);
+    }
+    DP_CHECK(ecap < (int64_t)2147483000, DP_ERR_INVALID, "edge capacity %lld exceeds int32 indexing", (long long)ecap);
+    p.Ecap = ecap;
+    std::vector<int> sample_of(p.N);
+    for (int b = 0; b < B; ++b) {
+        for (int i = poff[b]; i < poff[b + 1]; ++i) sample_of[i] = b;
+        for (int i = roff[b]; i < roff[b + 1]; ++i) sample_of[p.Np + i] = b;
+    }
+    auto& bag = p.allocations;
+    int rc = 0;
+    const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
+    const size_t units = (size_t)(ecap / UNIT_TC + 2);
+#define ALLOC(ptr, count) if ((rc = dev_alloc(bag, &(ptr), (size_t)(count)))) return rc
+    ALLOC(p.phar_off, B + 1); ALLOC(p.res_off, B + 1); ALLOC(p.sample_of, p.N);
+    ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1);
+    ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
+    ALLOC(p.counts, 4);
+    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.agg, (size_t)p.N * H);
+    ALLOC(p.partials, units * 2 * H);
+    ALLOC(p.pq, (size_t)p.N * 4 * H);
+    ALLOC(p.x_in, (size_t)p.N * 3); ALLOC(p.x_a, (size_t)p.N * 3); ALLOC(p.x_b, (size_t)p.N * 3);
+    ALLOC(p.z, (size_t)p.Np * PW); ALLOC(p.eps_hat, (size_t)p.Np * PW); ALLOC(p.pocket, (size_t)p.Nr * RW);
+    ALLOC(p.t_const, 4); ALLOC(p.step_idx, 1); ALLOC(p.nan_flag, 2);
+#undef ALLOC
+    DP_CUDA(cudaMemcpy(p.phar_off, poff.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(p.res_off, roff.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(p.sample_of, sample_of.data(), (size_t)p.N * sizeof(int), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemset(p.counts, 0, 4 * sizeof(int)));
+    DP_CUDA(cudaMemset(p.nan_flag, 0, 2 * sizeof(int)));
+    DP_CUDA(cudaMemset(p.step_idx, 0, sizeof(int)));
+    DP_CUDA(cudaMemset(p.t_const, 0, 4 * sizeof(float)));
+    h->has_plan = true;
+    if (h->n_steps > 0) {   // re-upload the step table into the new plan
+        std::vector<float> rows = h->step_rows_host;
+        float fin[4]; memcpy(fin, h->final_host, sizeof(fin));
+        return dp_set_step_table(h, rows.data(), h->n_steps, fin);
+    }
+    return DP_OK;
+}
+
+extern "C" int dp_set_step_table(dp_handle* h, const float* rows, int32_t n_steps, const float* fin)
+{
+    DP_CHECK(h && rows && fin && n_steps > 0, DP_ERR_INVALID, "dp_set_step_table: bad argument");
+    if (rows != h->step_rows_host.data()) h->step_rows_host.assign(rows, rows + (size_t)n_steps * 4);
+    memcpy(h->final_host, fin, 4 * sizeof(float));
+    h->n_steps = n_steps;
+    if (!h->has_plan) return DP_OK;
+    Plan& p = h->plan;
+    DP_CUDA(cudaSetDevice(h->device));
+    DP_CUDA(cudaDeviceSynchronize());
+    int rc = 0;
+    if ((rc = dev_alloc(p.allocations, &p.step_rows, (size_t)n_steps * 4))) return rc;
+    if ((rc = dev_alloc(p.allocations, &p.stats, (size_t)(n_steps + 2) * 2))) return rc;
+    p.stats_cap = n_steps + 2;
+    DP_CUDA(cudaMemcpy(p.step_rows, h->step_rows_host.data(), (size_t)n_steps * 4 * sizeof(float), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemset(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float)));
+    if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
+    return DP_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// graph
+// --------------------------------------------------------------------------------------
+static int require(dp_handle* h, bool weights, bool plan)
+{
+    DP_CHECK(h, DP_ERR_INVALID, "null handle");
+    DP_CHECK(!weights || h->has_weights, DP_ERR_STATE, "dp_set_weights has not been called");
+    DP_CHECK(!plan || h->has_plan, DP_ERR_STATE, "dp_plan has not been called");
+    DP_CUDA(cudaSetDevice(h->device));
+    return DP_OK;
+}
+
+extern "C" int dp_build_edges(dp_handle* h, const float* x_dev, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    DP_CHECK(x_dev, DP_ERR_INVALID, "dp_build_edges: null x");
+    return launch_build_edges(h, x_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dp_get_graph(dp_handle* h, const int32_t** rowptr, const int32_t** col, int64_t* n_edges, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    int counts[4];
+    DP_CUDA(cudaMemcpyAsync(counts, h->plan.counts, sizeof(counts), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    DP_CHECK(counts[2] == 0, DP_ERR_CAPACITY, "graph has %d edges but edge_capacity is %lld", counts[0], (long long)h->plan.Ecap);
+    if (rowptr) *rowptr = h->plan.rowptr;
+    if (col) *col = h->plan.col;
+    if (n_edges) *n_edges = counts[0];
+    return DP_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// one denoiser evaluation (EGNNDynamics.forward, dynamics.py:75-139)
+// --------------------------------------------------------------------------------------
+static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st)
+{
+    prof_begin(h, PROF_NODE, st);
+    int rc = (h->precision == DP_FP32) ? launch_linear_f32(h, a, st) : launch_linear_tc(h, a, lin_id, st);
+    prof_end(h, st);
+    return rc;
+}
+
+static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
+{
+    prof_begin(h, a.coord ? PROF_EDGE_COORD : PROF_EDGE_MSG, st);
+    int rc = (h->precision == DP_FP32) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
+    prof_end(h, st);
+    return rc;
+}
+
+// lin_id numbering for the tensor-core weight images: per GCL i: 4i+0 = edge_mlp.2, 4i+1 = node_mlp.0,
+// 4i+2 = node_mlp.2; per block b: 4G + b = coord_mlp.2; projections: 4G + L + v.
+static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
+                        const int* step_idx, int row_stride, int t_stride, float* out_phar, float* out_res,
+                        cudaStream_t st)
+{
+    Plan& p = h->plan; const dp_config& c = h->cfg; DeviceWeights& W = h->w;
+    const int S = c.inv_sublayers, G = c.n_layers * S;
+    const int unit = (h->precision == DP_FP32) ? UNIT_F32 : UNIT_TC;
+    int rc = 0;
+    if ((rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, st))) return rc;
+    if ((rc = launch_build_edges(h, p.x_in, st))) return rc;
+    float* x_cur = p.x_a; float* x_next = p.x_b;
+
+    auto project = [&](int v) -> int {
+        const ProjSet& ps = W.proj[v];
+        if (ps.lin.out == 0) return DP_OK;
+        LinearArgs a{};
+        a.x = p.h; a.ldx = H; a.two_source = 0; a.n_rows = p.N; a.K = H;
+        a.wt = ps.lin.wt; a.bias = ps.lin.b; a.n_out = ps.lin.out; a.y = p.pq; a.ldy = ps.lin.out; a.epi = 0;
+        return run_linear(h, a, 4 * G + c.n_layers + v, st);
+    };
+    AggView av{};
+    av.agg = p.agg; av.partials = p.partials; av.rowptr = p.rowptr; av.unit = unit;
+    av.norm = c.normalization_factor; av.inv_norm = 1.0f / c.normalization_factor; av.mean = c.aggregation_mean;
+
+    if ((rc = project(0))) return rc;
+    for (int i = 0; i < G; ++i) {
+        const GclWeights& L = W.gcl[i];
+        const ProjSet& pin = W.proj[i];
+        EdgeArgs e{};
+        e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
+        e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
+        e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
+        e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
+        e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh;
+        if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
+        // node model: h <- h + W4 silu(W3 [h | agg] + b3) + b4  (egnn_new.py:54-57)
+        LinearArgs n0{};
+        n0.x = p.h; n0.ldx = H; n0.two_source = 1; n0.aggv = av; n0.n_rows = p.N; n0.K = 2 * H;
+        n0.wt = L.n0.wt; n0.bias = L.n0.b; n0.n_out = H; n0.y = p.tbuf; n0.ldy = H; n0.epi = 1;
+        if ((rc = run_linear(h, n0, 4 * i + 1, st))) return rc;
+        LinearArgs n2{};
+        n2.x = p.tbuf; n2.ldx = H; n2.two_source = 0; n2.n_rows = p.N; n2.K = H;
+        n2.wt = L.n2.wt; n2.bias = L.n2.b; n2.n_out = H; n2.y = p.h; n2.ldy = H; n2.resid = p.h; n2.ldr = H; n2.epi = 2;
+        if ((rc = run_linear(h, n2, 4 * i + 2, st))) return rc;
+        if ((rc = project(i + 1))) return rc;
+        if ((i + 1) % S == 0) {
+            const int b = i / S;
+            const CoordWeights& Cw = W.coord[b];
+            const ProjSet& pc = W.proj[i + 1];
+            EdgeArgs q{};
+            q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
+            q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
+            q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
+            q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
+            q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh;
+            if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
+            prof_begin(h, PROF_EDGE_COORD, st);
+            rc = launch_coord_finish(h, x_cur, x_next, st);
+            prof_end(h, st);
+            if (rc) return rc;
+            float* t = x_cur; x_cur = x_next; x_next = t;
+        }
+    }
+    return launch_decode(h, x_cur, out_phar, out_res, st);
+}
+
+extern "C" int dp_dynamics_forward(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_dev,
+                                   int32_t t_stride, float* out_phar, float* out_res, void* stream)
+{
+    int rc = require(h, true, true);
+    if (rc) return rc;
+    DP_CHECK(xh_phar && xh_res && out_phar, DP_ERR_INVALID, "dp_dynamics_forward: null tensor");
+    DP_CHECK(t_dev || !h->cfg.condition_time, DP_ERR_INVALID, "dp_dynamics_forward: t is required");
+    DP_CHECK(t_stride == 0 || t_stride == 1, DP_ERR_INVALID, "t_stride must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = run_denoiser(h, xh_phar, xh_res, t_dev ? t_dev : h->plan.t_const, nullptr, 0, t_stride, out_phar, out_res, st))) return rc;
+    return launch_nan_fixup(h, out_phar, out_res, st);
+}
+
+// --------------------------------------------------------------------------------------
+// DDPM update + sampler loop
+// --------------------------------------------------------------------------------------
+extern "C" int dp_ddpm_update(dp_handle* h, int32_t kind, float a, float c, float sigma, float* z, float* pocket,
+                              const float* eps_hat, const float* noise, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    DP_CHECK(kind >= 0 && kind <= 2, DP_ERR_INVALID, "dp_ddpm_update: kind %d", kind);
+    DP_CHECK(z && pocket && noise && (eps_hat || kind == 2), DP_ERR_INVALID, "dp_ddpm_update: null tensor");
+    DdpmArgs d{};
+    d.kind = kind; d.a = a; d.c = c; d.sigma = sigma; d.table = nullptr; d.step_idx = nullptr;
+    d.z = z; d.pocket = pocket; d.eps_hat = eps_hat; d.noise = noise; d.stat_index = -1; d.advance = 0;
+    // the standalone call never saw the denoiser's NaN flag of another stream; clear semantics: caller's eps_hat
+    // already went through dp_dynamics_forward's fix-up, so the flag must not zero it again
+    DP_CUDA(cudaMemsetAsync(h->plan.nan_flag, 0, sizeof(int), (cudaStream_t)stream));
+    return launch_ddpm(h, d, (cudaStream_t)stream);
+}
+
+static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise, cudaStream_t st)
+{
+    Plan& p = h->plan; const dp_config& c = h->cfg;
+    const int PW = 3 + c.phar_nf;
+    int rc = run_denoiser(h, p.z, pocket, p.step_rows, p.step_idx, 4, 0, p.eps_hat, nullptr, st);
+    if (rc) return rc;
+    DdpmArgs d{};
+    d.kind = 0; d.table = p.step_rows; d.step_idx = p.step_idx;
+    d.z = p.z; d.pocket = pocket; d.eps_hat = p.eps_hat; d.noise = noise;
+    d.noise_step_stride = (int64_t)p.Np * PW; d.noise_step_base = 1;
+    d.stat_base = 0; d.stat_index = -1; d.advance = 1;
+    return launch_ddpm(h, d, st);
+}
+
+extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float* out_phar, void* stream)
+{
+    int rc = require(h, true, true);
+    if (rc) return rc;
+    DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
+    DP_CHECK(pocket && noise && out_phar, DP_ERR_INVALID, "dp_sample: null tensor");
+    Plan& p = h->plan; const dp_config& c = h->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int PW = 3 + c.phar_nf;
+    const size_t zbytes = (size_t)p.Np * PW * sizeof(float);
+    DP_CUDA(cudaMemsetAsync(p.step_idx, 0, sizeof(int), st));
+    DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
+    DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, sizeof(int), st));
+    // z_T ~ N(pocket COM, I), projected (conditional_model.py:412-418)
+    if ((rc = launch_pocket_com_init(h, p.z, pocket, st))) return rc;
+    DdpmArgs d0{};
+    d0.kind = 2; d0.sigma = 1.0f; d0.z = p.z; d0.pocket = pocket; d0.eps_hat = nullptr; d0.noise = noise;
+    d0.stat_index = -1; d0.advance = 0;
+    if ((rc = launch_ddpm(h, d0, st))) return rc;
+
+    if (h->profile) {
+        for (int k = 0; k < h->n_steps; ++k)
+            if ((rc = sampler_step_launches(h, pocket, noise, st))) return rc;
+    } else {
+        if (!p.step_graph || p.graph_noise != (void*)noise || p.graph_precision != h->precision ||
+            p.graph_pocket != (void*)pocket) {
+            if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
+            const int64_t before = h->launches;
+            cudaGraph_t g = nullptr;
+            DP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = sampler_step_launches(h, pocket, noise, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            DP_CUDA(ce);
+            p.graph_launches = h->launches - before;
+            h->launches = before;
+            DP_CUDA(cudaGraphInstantiate(&p.step_graph, g, 0));
+            cudaGraphDestroy(g);
+            p.graph_noise = (void*)noise; p.graph_precision = h->precision; p.graph_pocket = (void*)pocket;
+        }
+        for (int k = 0; k < h->n_steps; ++k) DP_CUDA(cudaGraphLaunch(p.step_graph, st));
+        h->launches += p.graph_launches * h->n_steps;
+    }
+    // p(x | z0): conditional_model.py:108-131
+    DP_CUDA(cudaMemcpyAsync(p.t_const, &h->final_host[0], sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = run_denoiser(h, p.z, pocket, p.t_const, nullptr, 0, 0, p.eps_hat, nullptr, st))) return rc;
+    DP_CUDA(cudaMemcpyAsync(out_phar, p.z, zbytes, cudaMemcpyDeviceToDevice, st));          // keeps z0's feature columns
+    DdpmArgs df{};
+    df.kind = 1; df.a = h->final_host[1]; df.c = h->final_host[2]; df.sigma = h->final_host[3];
+    df.z = p.z; df.pocket = pocket; df.eps_hat = p.eps_hat;
+    df.noise = noise + (size_t)(h->n_steps + 1) * p.Np * PW; df.stat_index = h->n_steps; df.advance = 0;
+    if ((rc = launch_ddpm(h, df, st))) return rc;
+    DP_CUDA(cudaMemcpy2DAsync(out_phar, PW * sizeof(float), p.z, PW * sizeof(float), 3 * sizeof(float), p.Np,
+                              cudaMemcpyDeviceToDevice, st));
+    return DP_OK;
+}
+
+extern "C" int dp_sample_host(dp_handle* h, const float* pocket_host, const float* noise_host, float* out_phar_host,
+                              float* pocket_out_host)
+{
+    int rc = require(h, true, true);
+    if (rc) return rc;
+    DP_CHECK(pocket_host && noise_host && out_phar_host, DP_ERR_INVALID, "dp_sample_host: null buffer");
+    Plan& p = h->plan; const dp_config& c = h->cfg;
+    const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
+    const size_t noise_count = (size_t)(h->n_steps + 2) * p.Np * PW;
+    if (!p.noise_buf || p.noise_buf_count < noise_count) {
+        if ((rc = dev_alloc(p.allocations, &p.noise_buf, noise_count))) return rc;
+        if (!p.out_buf && (rc = dev_alloc(p.allocations, &p.out_buf, (size_t)p.Np * PW))) return rc;
+        p.noise_buf_count = noise_count;
+    }
+    cudaStream_t st = 0;
+    DP_CUDA(cudaMemcpyAsync(p.pocket, pocket_host, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyHostToDevice, st));
+    DP_CUDA(cudaMemcpyAsync(p.noise_buf, noise_host, noise_count * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = dp_sample(h, p.pocket, p.noise_buf, p.out_buf, st))) return rc;
+    DP_CUDA(cudaMemcpyAsync(out_phar_host, p.out_buf, (size_t)p.Np * PW * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (pocket_out_host)
+        DP_CUDA(cudaMemcpyAsync(pocket_out_host, p.pocket, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DP_CUDA(cudaStreamSynchronize(st));
+    return DP_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// flags / counters / profiling
+// --------------------------------------------------------------------------------------
+extern "C" int dp_get_flags(dp_handle* h, dp_flags* out, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    DP_CHECK(out, DP_ERR_INVALID, "dp_get_flags: null out");
+    Plan& p = h->plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    int counts[4], nan[2];
+    DP_CUDA(cudaMemcpyAsync(counts, p.counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    DP_CUDA(cudaMemcpyAsync(nan, p.nan_flag, sizeof(nan), cudaMemcpyDeviceToHost, st));
+    std::vector<float> stats((size_t)p.stats_cap * 2, 0.f);
+    if (p.stats) DP_CUDA(cudaMemcpyAsync(stats.data(), p.stats, stats.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    DP_CUDA(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    out->nan_resets = nan[1];
+    out->edge_overflow = counts[2];
+    out->last_n_edges = counts[0];
+    out->last_n_edges_phar = counts[1];
+    float worst = 0.f;
+    for (int k = 0; k < p.stats_cap; ++k) {
+        const float rel = stats[2 * k] / (stats[2 * k + 1] + 1e-10f);
+        if (rel > worst) worst = rel;
+    }
+    out->max_mean_rel_err = worst;
+    out->last_max_cog = p.stats_cap ? stats[2 * (size_t)(p.stats_cap - 2)] : 0.f;
+    return DP_OK;
+}
+
+extern "C" int dp_reset_flags(dp_handle* h, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    Plan& p = h->plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    DP_CUDA(cudaMemsetAsync(p.counts + 2, 0, sizeof(int), st));
+    DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, 2 * sizeof(int), st));
+    if (p.stats) DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
+    return DP_OK;
+}
+
+extern "C" int64_t dp_launch_count(const dp_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int dp_profile_enable(dp_handle* h, int32_t on)
+{
+    DP_CHECK(h, DP_ERR_INVALID, "null handle");
+    h->profile = on != 0;
+    if (on) {
+        for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+        h->spans.clear();
+        for (int i = 0; i < 8; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    }
+    return DP_OK;
+}
+
+extern "C" int dp_profile_read(dp_handle* h, int32_t which, double* total_ms, int64_t* launches)
+{
+    DP_CHECK(h && which >= 0 && which < 8, DP_ERR_INVALID, "dp_profile_read: bad argument");
+    DP_CUDA(cudaSetDevice(h->device));
+    if (!h->spans.empty()) {
+        DP_CUDA(cudaDeviceSynchronize());
+        for (auto& s : h->spans) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { h->prof_ms[s.which] += ms; h->prof_n[s.which] += 1; }
+            cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+        }
+        cudaGetLastError();
+        h->spans.clear();
+    }
+    if (total_ms) *total_ms = h->prof_ms[which];
+    if (launches) *launches = h->prof_n[which];
+    return DP_OK;
+}

@@ -1,0 +1,254 @@
+// Internal declarations shared by the translation units of libdiffphar_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/diffphar_b200.h"
+
+constexpr int H = 256;            // hidden_nf (compile-time tile width)
+constexpr int UNIT_F32 = 64;      // edges per segmented-sum unit, FFMA path
+constexpr int UNIT_TC = 32;       // edges per segmented-sum unit, tcgen05 path
+
+void dp_set_error(const char* fmt, ...);
+
+#define DP_CUDA(expr)                                                                 \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            dp_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DP_ERR_CUDA;                                                       \
+        }                                                                             \
+    } while (0)
+
+#define DP_CHECK(cond, code, ...)                                                     \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            dp_set_error(__VA_ARGS__);                                                \
+            return (code);                                                            \
+        }                                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device-side math shared by kernels
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// Per-row aggregate assembled from the edge kernel's outputs.  A row whose edge range
+// [s,e) lies inside one segmented-sum unit was stored to agg[]; a row that crosses unit
+// boundaries was stored as per-unit partial sums (slot 0: segment containing the unit's
+// first edge, slot 1: the other boundary segment).  Summed here in unit order — no atomics.
+struct AggView {
+    const float* agg;        // [N][H] raw sums of complete rows
+    const float* partials;   // [units][2][H]
+    const int* rowptr;       // [N+1]
+    int unit;                // edges per unit
+    float inv_norm;          // 1/normalization_factor ('sum'); unused for 'mean'
+    float norm;              // normalization_factor
+    int mean;                // aggregation_method == 'mean'
+};
+
+__device__ __forceinline__ float4 agg_load4(const AggView& a, int row, int c)
+{
+    const int s = a.rowptr[row], e = a.rowptr[row + 1];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e > s) {
+        const int uf = s / a.unit, ul = (e - 1) / a.unit;
+        if (uf == ul) {
+            v = *reinterpret_cast<const float4*>(a.agg + (size_t)row * H + c);
+        } else {
+            for (int u = uf; u <= ul; ++u) {
+                const int slot = (s <= u * a.unit) ? 0 : 1;
+                const float4 p = *reinterpret_cast<const float4*>(a.partials + ((size_t)u * 2 + slot) * H + c);
+                v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+            }
+        }
+        // reference: result / normalization_factor (egnn_new.py:283-285) or / count (:287-291)
+        const float d = a.mean ? (float)(e - s) : a.norm;
+        v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// weights as laid out on the device
+// ---------------------------------------------------------------------------
+struct DevLinear {          // y = x W^T + b, stored transposed: wt[k * out + o]
+    float* wt = nullptr;
+    float* b = nullptr;     // may be null
+    int in = 0, out = 0;
+};
+
+struct GclWeights {
+    // edge_mlp.0 split: columns [0,H) act on h[row], [H,2H) on h[col], 2H on r2, 2H+1 on d0
+    float* wr = nullptr;    // [H]
+    float* wd = nullptr;    // [H]
+    DevLinear e2;           // edge_mlp.2
+    float* wa = nullptr;    // att_mlp.0 weight [H]
+    float ba = 0.f;
+    DevLinear n0, n2;       // node_mlp
+};
+
+struct CoordWeights {
+    float* wr = nullptr;
+    float* wd = nullptr;
+    DevLinear c2;
+    float* w4 = nullptr;    // coord_mlp.4 weight [H]
+};
+
+// A projection set: one GEMM h[N,H] -> PQ[N, n_out] feeding the next edge kernels.
+struct ProjSet {
+    DevLinear lin;          // in = H, out = 512 or 1024
+    int off_gcl = -1;       // column offset of (Pa|Pb) for the next GCL, -1 if none
+    int off_coord = -1;     // column offset of (Qa|Qb) for the coordinate update, -1 if none
+};
+
+struct DeviceWeights {
+    DevLinear phar_enc0, phar_enc2, phar_dec0, phar_dec2;
+    DevLinear res_enc0, res_enc2, res_dec0, res_dec2;
+    DevLinear emb, emb_out;
+    std::vector<GclWeights> gcl;       // n_layers * inv_sublayers
+    std::vector<CoordWeights> coord;   // n_layers
+    std::vector<ProjSet> proj;         // 1 + number of GCLs
+    std::vector<void*> allocations;
+};
+
+struct TcWeights;   // tcgen05 operand images (tc_path.cu)
+
+// ---------------------------------------------------------------------------
+// the plan: batch layout + workspace
+// ---------------------------------------------------------------------------
+struct Plan {
+    int B = 0, Np = 0, Nr = 0, N = 0;
+    int64_t Ecap = 0;
+    int max_phar = 0;
+    // layout
+    int* phar_off = nullptr;     // [B+1]
+    int* res_off = nullptr;      // [B+1]
+    int* sample_of = nullptr;    // [N]
+    // graph
+    int* deg = nullptr;          // [N]
+    int* rowptr = nullptr;       // [N+1]
+    int* col = nullptr;          // [Ecap]
+    int* erow = nullptr;         // [Ecap]
+    float* d0 = nullptr;         // [Ecap] squared input-frame distances (edge_attr, egnn_new.py:195)
+    int* counts = nullptr;       // [4]: E, E_p, overflow, spare
+    // node state
+    float* h = nullptr;          // [N][H]
+    float* tbuf = nullptr;       // [N][H] node-MLP hidden
+    float* agg = nullptr;        // [N][H]
+    float* partials = nullptr;   // [units][2][H]
+    float* pq = nullptr;         // [N][1024]
+    float* x_in = nullptr;       // [N][3]
+    float* x_a = nullptr;        // [N][3]
+    float* x_b = nullptr;        // [N][3]
+    float* escal = nullptr;      // [Ecap] coordinate-MLP scalar per edge
+    // sampler state
+    float* z = nullptr;          // [Np][3+P]
+    float* eps_hat = nullptr;    // [Np][3+P]
+    float* pocket = nullptr;     // [Nr][3+R]
+    float* t_const = nullptr;    // [1]
+    int* step_idx = nullptr;     // [1]
+    float* step_rows = nullptr;  // [n_steps][4]
+    float* stats = nullptr;      // [n_steps+2][2] (max |sum x|, max |x|) as float bits
+    int stats_cap = 0;
+    int* nan_flag = nullptr;     // [2]: current-call flag, sticky count
+    std::vector<void*> allocations;
+    cudaGraphExec_t step_graph = nullptr;
+    void* graph_noise = nullptr; // pointers baked into the captured graph
+    void* graph_pocket = nullptr;
+    int graph_precision = -1;
+    int64_t graph_launches = 0;  // kernels per replay of step_graph
+    // dp_sample_host staging
+    float* noise_buf = nullptr; size_t noise_buf_count = 0;
+    float* out_buf = nullptr;
+};
+
+struct dp_handle {
+    dp_config cfg;
+    int device = 0;
+    int sm_count = 148;
+    int precision = 0;
+    bool has_weights = false;
+    DeviceWeights w;
+    TcWeights* tc = nullptr;
+    Plan plan;
+    bool has_plan = false;
+    std::vector<float> step_rows_host;
+    float final_host[4] = {0, 0, 0, 0};
+    int n_steps = 0;
+    int64_t launches = 0;
+    // profiling
+    bool profile = false;
+    struct Span { int which; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double prof_ms[8] = {0};
+    int64_t prof_n[8] = {0};
+};
+
+enum ProfWhich { PROF_EDGE_MSG = 0, PROF_NODE = 1, PROF_EDGE_COORD = 2, PROF_GRAPH = 3, PROF_DDPM = 4, PROF_OTHER = 5 };
+
+// ---------------------------------------------------------------------------
+// kernel launchers (one per translation unit)
+// ---------------------------------------------------------------------------
+// graph.cu
+int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st);
+
+// egnn_f32.cu
+struct LinearArgs {
+    const float* x; int ldx;          // primary input rows
+    AggView aggv;                     // used when two_source
+    int two_source;                   // input = [x(0:H) | agg(0:H)], K = 2H
+    int n_rows; int K;
+    const float* wt; const float* bias; int n_out;
+    float* y; int ldy;
+    const float* resid; int ldr;      // epi 2: y = resid + acc + bias
+    int epi;                          // 0: +bias, 1: silu(+bias), 2: residual
+};
+int launch_linear_f32(dp_handle* h, const LinearArgs& a, cudaStream_t st);
+
+struct EdgeArgs {
+    const float* p; int ldp; int off_a; int off_b;   // pre-projected node features
+    const float* wr; const float* wd;                // [H] weights of the two edge scalars
+    const float* w2t; const float* b2;               // second layer, k-major [H][H]
+    const float* wv; float bv;                       // final vector: attention / coord_mlp.4
+    const float* x;                                  // current coordinates [N][3]
+    const float* d0; const int* erow; const int* ecol; const int* rowptr;
+    const int* n_edges;                              // device scalar: edges to process
+    float* agg; float* partials;                     // message outputs (coord == 0)
+    float* escal;                                    // per-edge scalar output (coord == 1)
+    int coord; int attention; int use_tanh;
+};
+int launch_edge_f32(dp_handle* h, const EdgeArgs& a, cudaStream_t st);
+int egnn_f32_init();
+
+// small.cu
+int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
+                        const int* step_idx, int row_stride, int t_stride, cudaStream_t st);
+int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStream_t st);
+int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* out_res, cudaStream_t st);
+int launch_nan_fixup(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st);
+struct DdpmArgs {
+    int kind; float a, c, sigma;              // immediate constants (table == null)
+    const float* table; const int* step_idx;  // or: row = table[*step_idx] = (t, a, c, sigma), kind 0
+    float* z; float* pocket; const float* eps_hat; const float* noise;
+    int64_t noise_step_stride;                // noise + (*step_idx + noise_step_base) * stride when table != null
+    int noise_step_base;
+    int stat_index;                           // stats row (table == null), else *step_idx + stat_base
+    int stat_base;
+    int advance;                              // 1: increment *step_idx afterwards (separate tiny kernel)
+};
+int launch_ddpm(dp_handle* h, const DdpmArgs& a, cudaStream_t st);
+int launch_pocket_com_init(dp_handle* h, float* z, const float* pocket, cudaStream_t st);
+
+// tc_path.cu (tcgen05)
+int tc_init();
+int tc_prepare_weights(dp_handle* h, const float* blob_host);
+void tc_free_weights(dp_handle* h);
+int launch_linear_tc(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);
+int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);
+
+// api.cu helpers
+void prof_begin(dp_handle* h, int which, cudaStream_t st);
+void prof_end(dp_handle* h, cudaStream_t st);

@@ -1,0 +1,362 @@
+// Prologue / epilogue / per-timestep kernels around the EGNN layers.
+//   encode_nodes   : type encoders + time column + EGNN.embedding   (dynamics.py:84-99, egnn_new.py:198)
+//   coord_finish   : coord_diff * scalar, row sum, masked x update    (egnn_new.py:91-103, 269-270)
+//   decode         : embedding_out, drop time column, type decoders, velocity, NaN flag
+//                                                                     (egnn_new.py:205, dynamics.py:110-131)
+//   ddpm           : K4 — mu arithmetic + noise + per-sample COM projection
+//                                                                     (conditional_model.py:136-156, 361-369, 467-475)
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+struct EncodeArgs {
+    const float* xh_phar; const float* xh_res;       // [Np][3+P], [Nr][3+R]
+    const float* t_base; const int* step_idx; int row_stride; int t_stride;
+    const int* sample_of;
+    int N, Np, P, R, J, D;                            // D = node_nf (J or J+1)
+    const float *pe0w, *pe0b, *pe2w, *pe2b;           // transposed [in][out]
+    const float *re0w, *re0b, *re2w, *re2b;
+    const float *embw, *embb;                         // [D][H], [H]
+    float* h; float* x_in; float* x_a; float* x_b;
+};
+
+__global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
+{
+    __shared__ float feat[64];     // raw type features (<= 64)
+    __shared__ float hid[128];     // 2 * nf hidden
+    __shared__ float joint[72];    // J (+1 time)
+    const int tid = threadIdx.x;
+    for (int node = blockIdx.x; node < a.N; node += gridDim.x) {
+        const bool phar = node < a.Np;
+        const int nf = phar ? a.P : a.R;
+        const float* src = phar ? a.xh_phar + (size_t)node * (3 + a.P) : a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
+        const float *w0 = phar ? a.pe0w : a.re0w, *b0 = phar ? a.pe0b : a.re0b;
+        const float *w2 = phar ? a.pe2w : a.re2w, *b2 = phar ? a.pe2b : a.re2b;
+        if (tid < nf) feat[tid] = src[3 + tid];
+        if (tid < 3) {
+            const float v = src[tid];
+            a.x_in[3 * node + tid] = v; a.x_a[3 * node + tid] = v; a.x_b[3 * node + tid] = v;
+        }
+        __syncthreads();
+        if (tid < 2 * nf) {
+            float acc = b0[tid];
+            for (int k = 0; k < nf; ++k) acc = fmaf(feat[k], w0[k * 2 * nf + tid], acc);
+            hid[tid] = silu_f(acc);
+        }
+        __syncthreads();
+        if (tid < a.J) {
+            float acc = b2[tid];
+            for (int k = 0; k < 2 * nf; ++k) acc = fmaf(hid[k], w2[k * a.J + tid], acc);
+            joint[tid] = acc;
+        }
+        if (tid == 0 && a.D > a.J) {
+            const int step = a.step_idx ? *a.step_idx : 0;
+            joint[a.J] = a.t_base[(size_t)step * a.row_stride + (size_t)a.sample_of[node] * a.t_stride];
+        }
+        __syncthreads();
+        {
+            float acc = a.embb[tid];
+            for (int k = 0; k < a.D; ++k) acc = fmaf(joint[k], a.embw[k * H + tid], acc);
+            a.h[(size_t)node * H + tid] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+struct CoordFinishArgs {
+    const float* x_cur; float* x_next; const float* escal;
+    const int* rowptr; const int* col;
+    int Np; float norm_constant, coords_range, norm_factor; int use_tanh, mean;
+};
+
+// One thread per phar row (the only rows update_coords_mask keeps, dynamics.py:105-107); the
+// row's edges are summed sequentially in CSR order, like the reference's index_add on CPU.
+__global__ void __launch_bounds__(128) coord_finish_kernel(CoordFinishArgs a)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.Np) return;
+    const int s = a.rowptr[r], e = a.rowptr[r + 1];
+    const float xi = a.x_cur[3 * r], yi = a.x_cur[3 * r + 1], zi = a.x_cur[3 * r + 2];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int k = s; k < e; ++k) {
+        const int j = a.col[k];
+        const float dx = xi - a.x_cur[3 * j], dy = yi - a.x_cur[3 * j + 1], dz = zi - a.x_cur[3 * j + 2];
+        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(r2, 1e-8f)), a.norm_constant);
+        const float v = a.escal[k];
+        float tx = __fmul_rn(__fdiv_rn(dx, nrm), v), ty = __fmul_rn(__fdiv_rn(dy, nrm), v), tz = __fmul_rn(__fdiv_rn(dz, nrm), v);
+        if (a.use_tanh) { tx = __fmul_rn(tx, a.coords_range); ty = __fmul_rn(ty, a.coords_range); tz = __fmul_rn(tz, a.coords_range); }
+        sx = __fadd_rn(sx, tx); sy = __fadd_rn(sy, ty); sz = __fadd_rn(sz, tz);
+    }
+    const float d = a.mean ? (float)max(e - s, 1) : a.norm_factor;
+    a.x_next[3 * r] = __fadd_rn(xi, __fdiv_rn(sx, d));
+    a.x_next[3 * r + 1] = __fadd_rn(yi, __fdiv_rn(sy, d));
+    a.x_next[3 * r + 2] = __fadd_rn(zi, __fdiv_rn(sz, d));
+}
+
+// ------------------------------------------------------------------------------------
+struct DecodeArgs {
+    const float* h; const float* x_final; const float* x_in;
+    int N, Np, P, R, J, D;
+    const float *eow, *eob;                           // embedding_out transposed [H][D], [D]
+    const float *pd0w, *pd0b, *pd2w, *pd2b;
+    const float *rd0w, *rd0b, *rd2w, *rd2b;
+    float* out_phar; float* out_res; int* nan_flag;
+    int n_nodes;                                      // Np, or N when out_res != null
+};
+
+__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a)
+{
+    __shared__ float hrow[H];
+    __shared__ float joint[64];
+    __shared__ float hid[128];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int node = blockIdx.x; node < a.n_nodes; node += gridDim.x) {
+        const bool phar = node < a.Np;
+        const int nf = phar ? a.P : a.R;
+        const float *w0 = phar ? a.pd0w : a.rd0w, *b0 = phar ? a.pd0b : a.rd0b;
+        const float *w2 = phar ? a.pd2w : a.rd2w, *b2 = phar ? a.pd2b : a.rd2b;
+        float* out = phar ? a.out_phar + (size_t)node * (3 + a.P) : a.out_res + (size_t)(node - a.Np) * (3 + a.R);
+        hrow[tid] = a.h[(size_t)node * H + tid];
+        __syncthreads();
+        // embedding_out rows 0..J-1 (the time column, row J, is dropped: dynamics.py:121-123)
+        for (int j = wid; j < a.J; j += 8) {
+            float part = 0.f;
+            for (int k = lane; k < H; k += 32) part = fmaf(hrow[k], a.eow[k * a.D + j], part);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) joint[j] = part + a.eob[j];
+        }
+        __syncthreads();
+        if (tid < 2 * nf) {
+            float acc = b0[tid];
+            for (int k = 0; k < a.J; ++k) acc = fmaf(joint[k], w0[k * 2 * nf + tid], acc);
+            hid[tid] = silu_f(acc);
+        }
+        __syncthreads();
+        if (tid < nf) {
+            float acc = b2[tid];
+            for (int k = 0; k < 2 * nf; ++k) acc = fmaf(hid[k], w2[k * nf + tid], acc);
+            out[3 + tid] = acc;
+        }
+        if (tid < 3) {
+            const float v = __fsub_rn(a.x_final[3 * node + tid], a.x_in[3 * node + tid]);   // dynamics.py:110
+            out[tid] = v;
+            if (v != v) a.nan_flag[0] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void nan_fixup_kernel(float* out_phar, float* out_res, int Np, int Nr, int P, int R, int* nan_flag)
+{
+    // dynamics.py:129-131 — a NaN anywhere in the velocity zeroes it for the whole batch
+    const bool bad = nan_flag[0] != 0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bad) {
+        if (i < Np) { out_phar[(size_t)i * (3 + P)] = 0.f; out_phar[(size_t)i * (3 + P) + 1] = 0.f; out_phar[(size_t)i * (3 + P) + 2] = 0.f; }
+        if (out_res && i < Nr) { out_res[(size_t)i * (3 + R)] = 0.f; out_res[(size_t)i * (3 + R) + 1] = 0.f; out_res[(size_t)i * (3 + R) + 2] = 0.f; }
+    }
+    if (i == 0 && bad) nan_flag[1] += 1;
+}
+
+__global__ void clear_flag_kernel(int* nan_flag) { nan_flag[0] = 0; }
+
+// ------------------------------------------------------------------------------------
+struct DdpmKArgs {
+    DdpmArgs d;
+    const int* phar_off; const int* res_off;
+    int P, R; int* nan_flag; float* stats;
+};
+
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v)
+{   // v >= 0: float order == int order; a guard statistic, not a data-path reduction
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+__global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
+{
+    extern __shared__ float buf[];             // [n_p][D] new values, then mean[3]
+    const DdpmArgs& d = k.d;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int D = 3 + k.P, RW = 3 + k.R;
+    const int p0 = k.phar_off[b], np = k.phar_off[b + 1] - p0;
+    const int r0 = k.res_off[b], nr = k.res_off[b + 1] - r0;
+    int kind = d.kind; float A = d.a, C = d.c, S = d.sigma;
+    const float* noise = d.noise;
+    int stat_row = d.stat_index;
+    if (d.table) {
+        const int step = *d.step_idx;
+        const float* row = d.table + 4 * (size_t)step;
+        kind = 0; A = row[1]; C = row[2]; S = row[3];
+        noise = d.noise + (size_t)(step + d.noise_step_base) * d.noise_step_stride;
+        stat_row = step + d.stat_base;
+    }
+    const bool nan = k.nan_flag[0] != 0;
+    float* mean = buf + (size_t)np * D;
+    for (int idx = tid; idx < np * D; idx += blockDim.x) {
+        const int c = idx % D;
+        const size_t g = (size_t)p0 * D + idx;
+        const float zt = d.z[g];
+        float mu;
+        if (kind == 2) mu = zt;
+        else {
+            float e = d.eps_hat[g];
+            if (nan && c < 3) e = 0.f;
+            if (kind == 0) mu = __fsub_rn(__fdiv_rn(zt, A), __fmul_rn(C, e));       // conditional_model.py:361-363
+            else mu = __fmul_rn(A, __fsub_rn(zt, __fmul_rn(C, e)));                  // en_diffusion.py:161
+        }
+        buf[idx] = __fadd_rn(mu, __fmul_rn(S, noise[g]));                            // conditional_model.py:147
+    }
+    __syncthreads();
+    if (tid < 3) {
+        // guard statistics on the INPUT state (assert_mean_zero_with_mask, conditional_model.py:372)
+        float sin_ = 0.f, amax = 0.f, tot = 0.f;
+        for (int i = 0; i < np; ++i) {
+            const float zi = d.z[(size_t)(p0 + i) * D + tid];
+            sin_ = __fadd_rn(sin_, zi); amax = fmaxf(amax, fabsf(zi));
+            tot = __fadd_rn(tot, buf[i * D + tid]);
+        }
+        mean[tid] = __fdiv_rn(tot, (float)max(np, 1));                               // scatter_mean
+        if (k.stats && stat_row >= 0 && kind != 2) {
+            atomic_max_pos(k.stats + 2 * stat_row, fabsf(sin_));
+            atomic_max_pos(k.stats + 2 * stat_row + 1, amax);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < np * D; idx += blockDim.x) {
+        const int c = idx % D;
+        float v = buf[idx];
+        if (c < 3) v = __fsub_rn(v, mean[c]);
+        d.z[(size_t)p0 * D + idx] = v;
+    }
+    for (int idx = tid; idx < nr * 3; idx += blockDim.x) {
+        const int i = idx / 3, c = idx - 3 * i;
+        float* px = d.pocket + (size_t)(r0 + i) * RW + c;
+        *px = __fsub_rn(*px, mean[c]);
+    }
+}
+
+__global__ void advance_step_kernel(int* step_idx) { step_idx[0] += 1; }
+
+// mu of the initial draw: pocket COM per sample, zero features (conditional_model.py:412-414)
+__global__ void __launch_bounds__(128) pocket_com_init_kernel(float* z, const float* pocket, const int* phar_off,
+                                                              const int* res_off, int P, int R)
+{
+    __shared__ float com[3];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int D = 3 + P, RW = 3 + R;
+    const int p0 = phar_off[b], np = phar_off[b + 1] - p0;
+    const int r0 = res_off[b], nr = res_off[b + 1] - r0;
+    if (tid < 3) {
+        float tot = 0.f;
+        for (int i = 0; i < nr; ++i) tot = __fadd_rn(tot, pocket[(size_t)(r0 + i) * RW + tid]);
+        com[tid] = __fdiv_rn(tot, (float)max(nr, 1));
+    }
+    __syncthreads();
+    for (int idx = tid; idx < np * D; idx += blockDim.x) {
+        const int c = idx % D;
+        z[(size_t)p0 * D + idx] = c < 3 ? com[c] : 0.f;
+    }
+}
+
+}  // namespace
+
+// ======================================================================================
+int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
+                        const int* step_idx, int row_stride, int t_stride, cudaStream_t st)
+{
+    const Plan& p = h->plan; const DeviceWeights& w = h->w; const dp_config& c = h->cfg;
+    EncodeArgs a;
+    a.xh_phar = xh_phar; a.xh_res = xh_res; a.t_base = t_base; a.step_idx = step_idx;
+    a.row_stride = row_stride; a.t_stride = t_stride; a.sample_of = p.sample_of;
+    a.N = p.N; a.Np = p.Np; a.P = c.phar_nf; a.R = c.residue_nf; a.J = c.joint_nf;
+    a.D = c.joint_nf + (c.condition_time ? 1 : 0);
+    a.pe0w = w.phar_enc0.wt; a.pe0b = w.phar_enc0.b; a.pe2w = w.phar_enc2.wt; a.pe2b = w.phar_enc2.b;
+    a.re0w = w.res_enc0.wt; a.re0b = w.res_enc0.b; a.re2w = w.res_enc2.wt; a.re2b = w.res_enc2.b;
+    a.embw = w.emb.wt; a.embb = w.emb.b;
+    a.h = p.h; a.x_in = p.x_in; a.x_a = p.x_a; a.x_b = p.x_b;
+    int grid = p.N < h->sm_count * 8 ? p.N : h->sm_count * 8;
+    if (grid < 1) grid = 1;
+    prof_begin(h, PROF_OTHER, st);
+    clear_flag_kernel<<<1, 1, 0, st>>>(p.nan_flag);
+    encode_nodes_kernel<<<grid, 256, 0, st>>>(a);
+    prof_end(h, st);
+    h->launches += 2;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    if (p.Np == 0) return DP_OK;
+    CoordFinishArgs a;
+    a.x_cur = x_cur; a.x_next = x_next; a.escal = p.escal; a.rowptr = p.rowptr; a.col = p.col;
+    a.Np = p.Np; a.norm_constant = c.norm_constant; a.coords_range = c.coords_range;
+    a.norm_factor = c.normalization_factor; a.use_tanh = c.use_tanh; a.mean = c.aggregation_mean;
+    coord_finish_kernel<<<(p.Np + 127) / 128, 128, 0, st>>>(a);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* out_res, cudaStream_t st)
+{
+    const Plan& p = h->plan; const DeviceWeights& w = h->w; const dp_config& c = h->cfg;
+    DecodeArgs a;
+    a.h = p.h; a.x_final = x_final; a.x_in = p.x_in;
+    a.N = p.N; a.Np = p.Np; a.P = c.phar_nf; a.R = c.residue_nf; a.J = c.joint_nf;
+    a.D = c.joint_nf + (c.condition_time ? 1 : 0);
+    a.eow = w.emb_out.wt; a.eob = w.emb_out.b;
+    a.pd0w = w.phar_dec0.wt; a.pd0b = w.phar_dec0.b; a.pd2w = w.phar_dec2.wt; a.pd2b = w.phar_dec2.b;
+    a.rd0w = w.res_dec0.wt; a.rd0b = w.res_dec0.b; a.rd2w = w.res_dec2.wt; a.rd2b = w.res_dec2.b;
+    a.out_phar = out_phar; a.out_res = out_res; a.nan_flag = p.nan_flag;
+    a.n_nodes = out_res ? p.N : p.Np;
+    if (a.n_nodes == 0) return DP_OK;
+    int grid = a.n_nodes < h->sm_count * 8 ? a.n_nodes : h->sm_count * 8;
+    prof_begin(h, PROF_OTHER, st);
+    decode_kernel<<<grid, 256, 0, st>>>(a);
+    prof_end(h, st);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_nan_fixup(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    const int n = p.Np > p.Nr ? p.Np : p.Nr;
+    nan_fixup_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(out_phar, out_res, p.Np, p.Nr, c.phar_nf, c.residue_nf, p.nan_flag);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_ddpm(dp_handle* h, const DdpmArgs& d, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    DdpmKArgs k;
+    k.d = d; k.phar_off = p.phar_off; k.res_off = p.res_off; k.P = c.phar_nf; k.R = c.residue_nf;
+    k.nan_flag = p.nan_flag; k.stats = p.stats;
+    const size_t smem = ((size_t)p.max_phar * (3 + c.phar_nf) + 4) * sizeof(float);
+    DP_CHECK(smem <= 48 * 1024, DP_ERR_INVALID, "ddpm: %d phar nodes in one sample exceed the shared-memory tile", p.max_phar);
+    prof_begin(h, PROF_DDPM, st);
+    ddpm_kernel<<<p.B, 128, smem, st>>>(k);
+    h->launches += 1;
+    if (d.advance) { advance_step_kernel<<<1, 1, 0, st>>>(p.step_idx); h->launches += 1; }
+    prof_end(h, st);
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_pocket_com_init(dp_handle* h, float* z, const float* pocket, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    pocket_com_init_kernel<<<p.B, 128, 0, st>>>(z, pocket, p.phar_off, p.res_off, c.phar_nf, c.residue_nf);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}

@@ -1,0 +1,253 @@
+"""Drop-in for DiffPhar/equivariant_diffusion/conditional_model.py::ConditionalDDPM —
+the sampling half (training losses are outside the accelerated path).
+
+``sample_given_pocket`` keeps the reference signature, return tuple, caller-dict mutation
+and assertion/print behaviour (conditional_model.py:388-465) but runs the whole reverse
+diffusion inside libdiffphar_b200.so: ONE call (dp_sample) replays a CUDA graph of the
+denoising step; the reference's per-step host syncs become device-side flags read once.
+The per-step methods (``sample_p_zs_given_zt`` ...) are kept for callers that drive the
+loop themselves; they call the same kernels one step at a time.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+from ..schedule import step_table
+from ..utils import num_nodes_to_batch_mask, scatter_add, scatter_mean
+from .en_diffusion import DistributionNodes, PredefinedNoiseSchedule, ScheduleMixin
+
+
+class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
+    def __init__(self, dynamics, phar_nf, residue_nf, n_dims, size_histogram, timesteps=1000,
+                 parametrization='eps', noise_schedule='learned', noise_precision=1e-4, loss_type='vlb',
+                 norm_values=(1., 1.), norm_biases=(None, 0.)):
+        super().__init__()
+        assert loss_type in {'vlb', 'l2'}
+        assert parametrization == 'eps'
+        if noise_schedule == 'learned':
+            raise NotImplementedError("learned noise schedules are outside the accelerated sampling path")
+        self.loss_type = loss_type
+        self.gamma = PredefinedNoiseSchedule(noise_schedule, timesteps=timesteps, precision=noise_precision)
+        self.dynamics = dynamics
+        self.phar_nf, self.residue_nf, self.n_dims = phar_nf, residue_nf, n_dims
+        self.num_classes = phar_nf
+        self.T = timesteps
+        self.parametrization = parametrization
+        self.norm_values, self.norm_biases = norm_values, norm_biases
+        self.register_buffer('buffer', torch.zeros(1))
+        self.size_distribution = DistributionNodes(size_histogram)
+        self._check_norm_values()
+        assert not self.dynamics.update_pocket_coords          # conditional_model.py:18
+        self._tables = {}
+
+    def _check_norm_values(self, num_stdevs=8):               # en_diffusion.py:64-77
+        g0 = self.gamma(torch.zeros((1, 1)))
+        sigma_0 = torch.sqrt(torch.sigmoid(g0)).item()
+        nv = self.norm_values[1]
+        if sigma_0 * num_stdevs > 1. / nv:
+            raise ValueError(f'Value for normalization value {nv} probably too large with sigma_0 '
+                             f'{sigma_0:.5f} and 1 / norm_value = {1. / nv}')
+
+    # ---------------------------------------------------------------- host glue
+    def normalize(self, phar=None, pocket=None):              # en_diffusion.py:874-889 (mutates the dicts)
+        for d in (phar, pocket):
+            if d is not None:
+                d['x'] = d['x'] / self.norm_values[0]
+                d['one_hot'] = (d['one_hot'].float() - self.norm_biases[1]) / self.norm_values[1]
+        return phar, pocket
+
+    def unnormalize(self, x, h_cat):
+        return x * self.norm_values[0], h_cat * self.norm_values[1] + self.norm_biases[1]
+
+    def unnormalize_z(self, z_phar, z_pocket):
+        nd = self.n_dims
+        xp, hp = self.unnormalize(z_phar[:, :nd], z_phar[:, nd:])
+        xk, hk = self.unnormalize(z_pocket[:, :nd], z_pocket[:, nd:])
+        return torch.cat([xp, hp], dim=1), torch.cat([xk, hk], dim=1)
+
+    @classmethod
+    def remove_mean_batch(cls, x_phar, x_pocket, phar_indices, pocket_indices):
+        mean = scatter_mean(x_phar, phar_indices)
+        return x_phar - mean[phar_indices], x_pocket - mean[pocket_indices]
+
+    @staticmethod
+    def assert_mean_zero_with_mask(x, node_mask, eps=1e-10):
+        largest = x.abs().max().item()
+        error = scatter_add(x, node_mask).abs().max().item()
+        rel = error / (largest + eps)
+        assert rel < 1e-2, f'Mean is not zero, relative_error {rel}'
+
+    @staticmethod
+    def sample_gaussian(size, device):
+        return torch.randn(size, device=device)
+
+    def _draw(self, n_draws, size, device):
+        """n_draws gaussian blocks.  If ``sample_gaussian`` was replaced on the instance
+        (noise injection, as the parity harness does) it is called once per draw in order."""
+        if 'sample_gaussian' in self.__dict__:
+            return torch.stack([self.sample_gaussian(size, device) for _ in range(n_draws)]).to(torch.float32)
+        return torch.randn((n_draws,) + tuple(size), device=device)
+
+    def _table(self, timesteps):
+        key = (timesteps, self.gamma.gamma.data_ptr(), self.gamma.gamma._version)
+        if key not in self._tables:
+            self._tables = {key: step_table(self.gamma.gamma, self.T, timesteps)}
+        return self._tables[key]
+
+    def _planned_handle(self, device, phar_mask, pocket_mask, n_samples):
+        h = self.dynamics.handle(device)
+        h.plan(self.dynamics._counts(phar_mask, n_samples), self.dynamics._counts(pocket_mask, n_samples))
+        return h
+
+    @staticmethod
+    def _scalar(v, what):
+        v = v.reshape(-1)
+        if v.numel() > 1 and not bool((v == v[0]).all()):
+            raise NotImplementedError(f"{what} differs across the batch; the fused DDPM update takes one "
+                                      "constant per step (all samples share s and t while sampling)")
+        return float(v[0])
+
+    # ---------------------------------------------------------------- per-step API
+    def compute_x_pred(self, net_out, zt, gamma_t, batch_mask):      # en_diffusion.py:153-165
+        sigma_t = self.sigma(gamma_t, target_tensor=net_out)
+        alpha_t = self.alpha(gamma_t, target_tensor=net_out)
+        return 1. / alpha_t[batch_mask] * (zt - sigma_t[batch_mask] * net_out)
+
+    def sample_normal(self, *args):
+        raise NotImplementedError("Has been replaced by sample_normal_zero_com()")
+
+    def sample_combined_position_feature_noise(self, *args):
+        raise NotImplementedError("Use sample_normal_zero_com() instead.")
+
+    def sample(self, *args):
+        raise NotImplementedError("Conditional model does not support sampling without given pocket.")
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training losses are outside the accelerated sampling path")
+
+    def sample_normal_zero_com(self, mu_phar, xh0_pocket, sigma, phar_mask, pocket_mask, fix_noise=False):
+        if fix_noise:
+            raise NotImplementedError("fix_noise option isn't implemented yet")
+        dev = mu_phar.device
+        n_samples = int(max(int(phar_mask.max()), int(pocket_mask.max()))) + 1
+        h = self._planned_handle(dev, phar_mask, pocket_mask, n_samples)
+        eps = self.sample_gaussian(size=(len(phar_mask), self.n_dims + self.phar_nf), device=phar_mask.device)
+        z = mu_phar.detach().to(torch.float32).contiguous().clone()
+        pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
+        sig = self._scalar(torch.as_tensor(sigma, dtype=torch.float32), "sigma")
+        h.ddpm_update(2, 1.0, 0.0, sig, z, pocket, None, eps)
+        return z, pocket
+
+    def sample_p_zs_given_zt(self, s, t, zt_phar, xh0_pocket, phar_mask, pocket_mask, fix_noise=False):
+        if fix_noise:
+            raise NotImplementedError("fix_noise option isn't implemented yet")
+        gamma_s, gamma_t = self.gamma(s), self.gamma(t)
+        sigma2_ts, sigma_ts, alpha_ts = self.sigma_and_alpha_t_given_s(gamma_t, gamma_s, zt_phar)
+        sigma_s = self.sigma(gamma_s, target_tensor=zt_phar)
+        sigma_t = self.sigma(gamma_t, target_tensor=zt_phar)
+        c_eps = sigma2_ts / alpha_ts / sigma_t
+        sigma = sigma_ts * sigma_s / sigma_t
+        n_samples = int(s.shape[0])
+        h = self._planned_handle(zt_phar.device, phar_mask, pocket_mask, n_samples)
+        eps_hat, _ = h.dynamics_forward(zt_phar, xh0_pocket, t.to(torch.float32), want_residues=False)
+        eps = self.sample_gaussian(size=(len(phar_mask), self.n_dims + self.phar_nf), device=phar_mask.device)
+        self.assert_mean_zero_with_mask(zt_phar[:, :self.n_dims], phar_mask)
+        z = zt_phar.detach().to(torch.float32).contiguous().clone()
+        pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
+        h.ddpm_update(0, self._scalar(alpha_ts, "alpha_t|s"), self._scalar(c_eps, "sigma2/alpha/sigma"),
+                      self._scalar(sigma, "sigma"), z, pocket, eps_hat, eps)
+        return z, pocket
+
+    def sample_p_xh_given_z0(self, z0_phar, xh0_pocket, phar_mask, pocket_mask, batch_size, fix_noise=False):
+        if fix_noise:
+            raise NotImplementedError("fix_noise option isn't implemented yet")
+        dev = z0_phar.device
+        t_zeros = torch.zeros(size=(batch_size, 1), device=dev)
+        gamma_0 = self.gamma(t_zeros)
+        sigma_x = self.SNR(-0.5 * gamma_0)
+        h = self._planned_handle(dev, phar_mask, pocket_mask, batch_size)
+        eps_hat, _ = h.dynamics_forward(z0_phar, xh0_pocket, t_zeros, want_residues=False)
+        net = eps_hat
+        inv_alpha0 = 1. / self.alpha(gamma_0, target_tensor=net)
+        sigma0 = self.sigma(gamma_0, target_tensor=net)
+        eps = self.sample_gaussian(size=(len(phar_mask), self.n_dims + self.phar_nf), device=phar_mask.device)
+        z = z0_phar.detach().to(torch.float32).contiguous().clone()
+        pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
+        h.ddpm_update(1, self._scalar(inv_alpha0, "1/alpha_0"), self._scalar(sigma0, "sigma_0"),
+                      self._scalar(sigma_x, "sigma_x"), z, pocket, eps_hat, eps)
+        nd = self.n_dims
+        x_phar, h_phar = self.unnormalize(z[:, :nd], z0_phar[:, nd:])
+        x_pocket, h_pocket = self.unnormalize(pocket[:, :nd], pocket[:, nd:])
+        h_phar = F.one_hot(torch.argmax(h_phar, dim=1), self.phar_nf)
+        return x_phar, h_phar, x_pocket, h_pocket
+
+    # ---------------------------------------------------------------- the sampler
+    @torch.no_grad()
+    def sample_given_pocket(self, pocket, num_nodes_phar, return_frames=1, timesteps=None):
+        timesteps = self.T if timesteps is None else timesteps
+        assert 0 < return_frames <= timesteps
+        assert timesteps % return_frames == 0
+        n_samples = len(pocket['size'])
+        device = pocket['x'].device
+        nd = self.n_dims
+
+        _, pocket = self.normalize(pocket=pocket)
+        xh0_pocket = torch.cat([pocket['x'], pocket['one_hot']], dim=1)
+        phar_mask = num_nodes_to_batch_mask(n_samples, num_nodes_phar, device)
+        if return_frames != 1:
+            return self._sample_with_frames(pocket, xh0_pocket, phar_mask, n_samples, return_frames, timesteps)
+
+        h = self._planned_handle(device, phar_mask, pocket['mask'], n_samples)
+        tab = self._table(timesteps)
+        h.set_step_table(tab.rows, tab.final)
+        noise = self._draw(timesteps + 2, (len(phar_mask), nd + self.phar_nf), device)
+        xh_pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
+        out = h.sample(xh_pocket, noise)                      # [N_p, 3+P] = (x_final | z0 features)
+
+        fl = h.flags()                                        # ONE host read for the whole run
+        if fl.edge_overflow:
+            raise _lib.DiffPharError("edge buffer overflow: re-plan with a larger edge_capacity")
+        if fl.nan_resets:
+            print('Warning: detected nan, resetting EGNN output to zero.')
+        assert fl.max_mean_rel_err < 1e-2, f'Mean is not zero, relative_error {fl.max_mean_rel_err}'
+        h.reset_flags()
+
+        x_phar, h_phar = self.unnormalize(out[:, :nd], out[:, nd:])
+        x_pocket, h_pocket = self.unnormalize(xh_pocket[:, :nd], xh_pocket[:, nd:])
+        h_phar = F.one_hot(torch.argmax(h_phar, dim=1), self.phar_nf)
+        self.assert_mean_zero_with_mask(x_phar, phar_mask)
+        max_cog = scatter_add(x_phar, phar_mask).abs().max().item()
+        if max_cog > 5e-2:
+            print(f'Warning CoG drift with error {max_cog:.3f}. Projecting the positions down.')
+            x_phar, x_pocket = self.remove_mean_batch(x_phar, x_pocket, phar_mask, pocket['mask'])
+        out_phar = torch.cat([x_phar, h_phar.to(x_phar.dtype)], dim=1)
+        out_pocket = torch.cat([x_pocket, h_pocket], dim=1)
+        return out_phar, out_pocket, phar_mask, pocket['mask']
+
+    def _sample_with_frames(self, pocket, xh0_pocket, phar_mask, n_samples, return_frames, timesteps):
+        """return_frames > 1: the loop is driven from the host, one fused step at a time."""
+        device = xh0_pocket.device
+        nd = self.n_dims
+        mu_x = scatter_mean(pocket['x'], pocket['mask'])
+        mu_h = torch.zeros((n_samples, self.phar_nf), device=device)
+        mu = torch.cat((mu_x, mu_h), dim=1)[phar_mask]
+        sigma = torch.ones(1, device=device)
+        z, xh_pocket = self.sample_normal_zero_com(mu, xh0_pocket, sigma, phar_mask, pocket['mask'])
+        self.assert_mean_zero_with_mask(z[:, :nd], phar_mask)
+        out_phar = torch.zeros((return_frames,) + z.size(), device=device)
+        out_pocket = torch.zeros((return_frames,) + xh_pocket.size(), device=device)
+        for s in reversed(range(0, timesteps)):
+            s_array = torch.full((n_samples, 1), fill_value=s, device=device)
+            t_array = (s_array + 1) / timesteps
+            s_array = s_array / timesteps
+            z, xh_pocket = self.sample_p_zs_given_zt(s_array, t_array, z, xh_pocket, phar_mask, pocket['mask'])
+            if (s * return_frames) % timesteps == 0:
+                idx = (s * return_frames) // timesteps
+                out_phar[idx], out_pocket[idx] = self.unnormalize_z(z, xh_pocket)
+        x_phar, h_phar, x_pocket, h_pocket = self.sample_p_xh_given_z0(z, xh_pocket, phar_mask, pocket['mask'], n_samples)
+        self.assert_mean_zero_with_mask(x_phar, phar_mask)
+        out_phar[0] = torch.cat([x_phar, h_phar], dim=1)
+        out_pocket[0] = torch.cat([x_pocket, h_pocket], dim=1)
+        return out_phar.squeeze(0), out_pocket.squeeze(0), phar_mask, pocket['mask']

@@ -164,8 +164,24 @@ def gen_schedule():
     print("schedule ok")
 
 
+def gen_state_keys():
+    """The weight ABI: state-dict keys + shapes of the reference modules."""
+    import json
+    out = {}
+    for name in CASES:
+        cfg = DynamicsConfig(**CASES[name][0])
+        ddpm = ref_shims.build_reference_model(cfg, init_weights(cfg, CASES[name][4]), T=500)
+        out[name] = {"dynamics": {k: list(v.shape) for k, v in ddpm.dynamics.state_dict().items()},
+                     "ddpm_extra": {k: list(v.shape) for k, v in ddpm.state_dict().items()
+                                    if not k.startswith("dynamics.")}}
+    with open(os.path.join(OUT, "state_keys.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("state keys ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gen_state_keys()
     torch.set_num_threads(8)
     gen_schedule()
     for name in CASES:

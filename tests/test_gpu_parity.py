@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden
+fixtures produced by the unmodified reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (fp32 mode; stated per north_star):
+  * CSR edges / degrees: bit-exact.
+  * denoiser feature channels: |err| <= 2e-5 * max(1, |ref|_max)   (reference fp32 itself: ~1e-7)
+  * denoiser coordinate channels: ABSOLUTE, |err| <= 1e-5 * max(1, |x|_max) — vel = x_out - x
+    cancels at coordinate magnitude, so a relative bound is meaningless.
+  * DDPM update: bit-exact against the fp32 oracle.
+  * end-to-end sample: coordinates within max(10x the reference's own fp32-vs-fp64 error,
+    1e-4 * coordinate scale); types identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cmd_gen_b200 import _lib
+from cmd_gen_b200.config import DynamicsConfig
+from cmd_gen_b200.schedule import gamma_table, step_table
+from cmd_gen_b200.synthetic import make_pocket_batch, draw_noise
+from cmd_gen_b200.weights import init_weights, pack_blob
+from oracle import diffphar_oracle as orc
+from tests.helpers import case_config, load, T
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
+
+
+def make_handle(cfg, wseed, precision="fp32"):
+    h = _lib.Handle(cfg, DEV, precision)
+    h.set_weights(pack_blob(cfg, init_weights(cfg, wseed)))
+    return h
+
+
+def csr_to_coo(rowptr, col):
+    rowptr, col = rowptr.cpu().long(), col.cpu().long()
+    deg = rowptr[1:] - rowptr[:-1]
+    row = torch.repeat_interleave(torch.arange(deg.numel()), deg)
+    return torch.stack([row, col]).numpy()
+
+
+# ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("name", CASES)
+def test_edges_bit_exact_vs_reference(name):
+    g = load(f"dynamics_{name}.npz")
+    cfg = case_config(name)
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["sizes"])
+    x = torch.cat([T(g["z"])[:, :3], T(g["xh_pocket"])[:, :3]]).to(DEV)
+    rowptr, col = h.build_edges(x)
+    assert np.array_equal(csr_to_coo(rowptr, col), g["edges_ref"])
+    ref_deg = np.bincount(g["edges_ref"][0], minlength=x.shape[0])
+    assert np.array_equal((rowptr[1:] - rowptr[:-1]).cpu().numpy(), ref_deg)
+
+
+@pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.05, 700, 12, 6)])
+def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B):
+    cfg = DynamicsConfig(residue_nf=20)
+    h = make_handle(DynamicsConfig(n_layers=1), 0)
+    pocket = make_pocket_batch([n_res], 20, density=density, seed=5, replicate=B)
+    gen = torch.Generator().manual_seed(9)
+    com = pocket["x"][:n_res].mean(0)
+    xp = com + 6.0 * torch.randn(B * n_phar, 3, generator=gen)
+    x = torch.cat([xp, pocket["x"]])
+    mask = torch.cat([torch.repeat_interleave(torch.arange(B), n_phar), pocket["mask"]])
+    h.plan([n_phar] * B, [n_res] * B)
+    rowptr, col = h.build_edges(x.to(DEV))
+    ref = orc.exact_edges(mask, x, cfg.edge_cutoff).numpy()
+    got = csr_to_coo(rowptr, col)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    # symmetric, self loops present, sorted
+    s = set(map(tuple, got.T.tolist()))
+    assert all((c, r) in s for r, c in list(s)[:2000])
+    fl = h.flags()
+    assert fl.last_n_edges == ref.shape[1] and fl.edge_overflow == 0
+    assert fl.last_n_edges_phar == int((ref[0] < B * n_phar).sum())
+
+
+def test_edge_capacity_overflow_is_reported():
+    h = make_handle(DynamicsConfig(n_layers=1), 0)
+    h.plan([2], [40], edge_capacity=50)
+    x = torch.zeros(42, 3, device=DEV)        # all nodes coincide: 42*42 edges
+    with pytest.raises(_lib.DiffPharError):
+        h.build_edges(x)
+
+
+# ----------------------------------------------------------------------------- denoiser
+@pytest.mark.parametrize("name", CASES)
+def test_dynamics_fp32_vs_reference(name):
+    g = load(f"dynamics_{name}.npz")
+    cfg = case_config(name)
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["sizes"])
+    B = len(g["sizes"])
+    xs = max(1.0, float(np.abs(g["z"][:, :3]).max()))
+    for i, tv in enumerate(g["t_values"]):
+        t = torch.full((B,), float(tv))
+        out_p, out_r = h.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), t)
+        out_p, out_r = out_p.cpu().numpy(), out_r.cpu().numpy()
+        rp, rr = g[f"eps_phar_f64_{i}"], g[f"eps_res_f64_{i}"]
+        assert np.abs(out_p[:, :3] - rp[:, :3]).max() <= 1e-5 * xs
+        assert np.abs(out_p[:, 3:] - rp[:, 3:]).max() <= 2e-5 * max(1.0, np.abs(rp[:, 3:]).max())
+        assert np.abs(out_r[:, 3:] - rr[:, 3:]).max() <= 2e-5 * max(1.0, np.abs(rr[:, 3:]).max())
+        assert np.all(out_r[:, :3] == 0.0)                  # pocket nodes never move
+    out_p, _ = h.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), torch.tensor([0.25]))
+    assert np.abs(out_p.cpu().numpy()[:, 3:] - g["eps_phar_f32_scalar_t"][:, 3:]).max() <= 2e-5
+    assert h.flags().nan_resets == 0
+
+
+def test_dynamics_module_api_and_kwargs():
+    from cmd_gen_b200.equivariant_diffusion.dynamics import EGNNDynamics
+    g = load("dynamics_ca_small.npz")
+    cfg = case_config("ca_small")
+    dyn = EGNNDynamics(8, 20, 3, joint_nf=32, hidden_nf=256, device=DEV, n_layers=5, attention=True, tanh=True,
+                       norm_constant=1, inv_sublayers=1, update_pocket_coords=False, edge_cutoff=6.0)
+    dyn.load_state_dict(init_weights(cfg, int(g["wseed"])))
+    z, xr = T(g["z"]).to(DEV), T(g["xh_pocket"]).to(DEV)
+    mp, mr = T(g["mask_phar"]).to(DEV), T(g["mask_res"]).to(DEV)
+    t = torch.full((3, 1), 0.5, device=DEV)
+    a, b = dyn(z, xr, t, mp, mr)
+    a2, _ = dyn(xh_atoms=z, xh_residues=xr, t=t, mask_atoms=mp, mask_residues=mr)
+    assert torch.equal(a, a2)
+    ref = g["eps_phar_f64_1"]
+    assert np.abs(a.cpu().numpy()[:, 3:] - ref[:, 3:]).max() <= 2e-5 * max(1.0, np.abs(ref[:, 3:]).max())
+    e = dyn.get_edges(torch.cat([mp, mr]), torch.cat([z[:, :3], xr[:, :3]]))
+    assert e.dtype == torch.int64 and np.array_equal(e.cpu().numpy(), g["edges_ref"])
+    with pytest.raises(NotImplementedError):
+        dyn(z, xr, t, mp.flip(0), mr)
+
+
+def test_nan_guard_zeroes_velocity_for_whole_batch():
+    g = load("dynamics_ca_small.npz")
+    cfg = case_config("ca_small")
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["sizes"])
+    z = T(g["z"]).clone()
+    z[0, 4] = float("nan")                                # poisons h of one phar node -> NaN velocity
+    out_p, out_r = h.dynamics_forward(z, T(g["xh_pocket"]), torch.full((3,), 0.5))
+    assert h.flags().nan_resets == 1
+    assert torch.all(out_p[:, :3] == 0) and torch.all(out_r[:, :3] == 0)
+
+
+def test_rotation_translation_equivariance_full_size():
+    """Size-independent property at config-2 size (B=64, N=10112): features invariant,
+    velocities rotate with the frame."""
+    cfg = DynamicsConfig()
+    h = make_handle(cfg, 0)
+    B, n_res, n_ph = 64, 150, 8
+    pocket = make_pocket_batch([n_res], 20, seed=3, replicate=B)
+    gen = torch.Generator().manual_seed(4)
+    com = pocket["x"][:n_res].mean(0)
+    z = torch.cat([com + 5.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(B * n_ph, 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    h.plan([n_ph] * B, [n_res] * B)
+    t = torch.full((B,), 0.4)
+    a, _ = h.dynamics_forward(z, xr, t, want_residues=False)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=torch.float64))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    q = q.float()
+    shift = torch.tensor([3.0, -2.0, 1.5])
+    z2, xr2 = z.clone(), xr.clone()
+    z2[:, :3] = (z[:, :3] - com) @ q.T + com + shift
+    xr2[:, :3] = (xr[:, :3] - com) @ q.T + com + shift
+    b, _ = h.dynamics_forward(z2, xr2, t, want_residues=False)
+    a, b = a.cpu(), b.cpu()
+    assert h.flags().last_n_edges > 50000
+    assert (a[:, 3:] - b[:, 3:]).abs().max() <= 5e-4 * max(1.0, a[:, 3:].abs().max())
+    vmax = float(a[:, :3].abs().max())
+    assert vmax > 1e-5
+    assert (a[:, :3] @ q.T - b[:, :3]).abs().max() <= 0.05 * vmax + 1e-5
+
+
+# ----------------------------------------------------------------------------- K4
+def test_ddpm_update_bit_exact_vs_oracle():
+    g = load("dynamics_ca_small.npz")
+    cfg = case_config("ca_small")
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["sizes"])
+    z, xr = T(g["z"]), T(g["xh_pocket"])
+    mp, mr = T(g["mask_phar"]), T(g["mask_res"])
+    eps_hat = T(g["eps_phar_f32_1"])
+    noise = draw_noise(1, z.shape[0], 11, seed=77)[0]
+    a, c, s = np.float32(1.6101650), np.float32(0.9891156), np.float32(0.78376114)
+    # same-shape tensors, like the reference's [N_p,1] constants (tensor / tensor is a true division)
+    at, ct = torch.full((z.shape[0], 1), float(a)), torch.full((z.shape[0], 1), float(c))
+    # kind 0
+    mu = z / at - ct * eps_hat
+    ref_z, ref_p = orc.noise_and_center(mu, xr, torch.tensor(s), noise, mp, mr, 3)
+    zd, pd = z.to(DEV).clone(), xr.to(DEV).clone()
+    h.ddpm_update(0, a, c, s, zd, pd, eps_hat, noise)
+    assert torch.equal(zd.cpu(), ref_z) and torch.equal(pd.cpu(), ref_p)
+    # kind 1
+    mu = at * (z - ct * eps_hat)
+    ref_z, ref_p = orc.noise_and_center(mu, xr, torch.tensor(s), noise, mp, mr, 3)
+    zd, pd = z.to(DEV).clone(), xr.to(DEV).clone()
+    h.ddpm_update(1, a, c, s, zd, pd, eps_hat, noise)
+    assert torch.equal(zd.cpu(), ref_z) and torch.equal(pd.cpu(), ref_p)
+    # kind 2
+    ref_z, ref_p = orc.noise_and_center(z, xr, torch.tensor(1.0), noise, mp, mr, 3)
+    zd, pd = z.to(DEV).clone(), xr.to(DEV).clone()
+    h.ddpm_update(2, 1.0, 0.0, 1.0, zd, pd, None, noise)
+    assert torch.equal(zd.cpu(), ref_z) and torch.equal(pd.cpu(), ref_p)
+
+
+# ----------------------------------------------------------------------------- sampler
+def build_ddpm(cfg, wseed, Tn, precision="fp32"):
+    from cmd_gen_b200.equivariant_diffusion.dynamics import EGNNDynamics
+    from cmd_gen_b200.equivariant_diffusion.conditional_model import ConditionalDDPM
+    dyn = EGNNDynamics(cfg.phar_nf, cfg.residue_nf, 3, joint_nf=cfg.joint_nf, hidden_nf=256, device=DEV,
+                       n_layers=cfg.n_layers, attention=cfg.attention, tanh=cfg.tanh,
+                       norm_constant=cfg.norm_constant, inv_sublayers=cfg.inv_sublayers,
+                       update_pocket_coords=False, edge_cutoff=cfg.edge_cutoff, precision=precision)
+    dyn.load_state_dict(init_weights(cfg, wseed))
+    ddpm = ConditionalDDPM(dyn, cfg.phar_nf, cfg.residue_nf, 3, [[1.0, 1.0], [1.0, 1.0]], timesteps=Tn,
+                           noise_schedule="polynomial_2", noise_precision=1e-5, loss_type="l2",
+                           norm_values=(1.0, 4.0)).to(DEV)
+    return ddpm
+
+
+def inject(ddpm, noise):
+    it = iter(noise)
+    ddpm.sample_gaussian = lambda size, device: next(it).to(device)
+
+
+@pytest.mark.parametrize("fixture,name", [("sampler_ca_small_T500_n12.npz", "ca_small"),
+                                          ("sampler_ca_small_T20.npz", "ca_small"),
+                                          ("sampler_fa_small_T500_n6.npz", "fa_small")])
+def test_sample_given_pocket_vs_reference(fixture, name):
+    g = load(fixture)
+    cfg = case_config(name)
+    Tn = int(g["T"])
+    ts = None if int(g["timesteps"]) < 0 else int(g["timesteps"])
+    ddpm = build_ddpm(cfg, int(g["wseed"]), Tn)
+    inject(ddpm, T(g["noise"]))
+    pocket = {"x": T(g["pocket_x"]).to(DEV), "one_hot": T(g["pocket_one_hot"]).to(DEV),
+              "size": T(g["pocket_size"]).to(DEV), "mask": T(g["pocket_mask"]).to(DEV)}
+    x_before = pocket["x"].clone()
+    xh_phar, xh_pocket, mp, mr = ddpm.sample_given_pocket(pocket, T(g["counts"]), timesteps=ts)
+    assert pocket["one_hot"].dtype == torch.float32           # caller's dict mutated by normalize()
+    assert torch.equal(pocket["x"], x_before / 1.0)
+    assert np.array_equal(mp.cpu().numpy(), g["mask_phar"])
+    scale = np.abs(g["xh_phar_f64"][:, :3]).max()
+    ref_err = np.abs(g["xh_phar_f32"][:, :3] - g["xh_phar_f64"][:, :3]).max()
+    err = np.abs(xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]).max()
+    assert err <= max(10 * ref_err, 1e-4 * scale), (err, ref_err, scale)
+    assert np.array_equal(xh_phar.cpu().numpy()[:, 3:], g["xh_phar_f32"][:, 3:])
+    perr = np.abs(xh_pocket.cpu().numpy() - g["xh_pocket_f64"]).max()
+    assert perr <= max(10 * ref_err, 1e-4 * scale)
+    # per-sample RMSD (north_star's end-to-end criterion)
+    d = xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]
+    for b in np.unique(g["mask_phar"]):
+        rmsd = np.sqrt((d[g["mask_phar"] == b] ** 2).sum(1).mean())
+        assert rmsd <= max(10 * ref_err, 1e-4 * scale)
+
+
+def test_per_step_api_follows_reference_trace():
+    g = load("sampler_ca_small_T500_n12.npz")
+    cfg = case_config("ca_small")
+    ddpm = build_ddpm(cfg, int(g["wseed"]), 500)
+    inject(ddpm, T(g["noise"]))
+    pocket = {"x": T(g["pocket_x"]).to(DEV), "one_hot": T(g["pocket_one_hot"]).to(DEV),
+              "size": T(g["pocket_size"]).to(DEV), "mask": T(g["pocket_mask"]).to(DEV)}
+    out_phar, out_pocket, mp, mr = ddpm.sample_given_pocket(pocket, T(g["counts"]), return_frames=2, timesteps=12)
+    assert out_phar.shape[0] == 2
+    scale = np.abs(g["xh_phar_f64"][:, :3]).max()
+    ref_err = np.abs(g["xh_phar_f32"][:, :3] - g["xh_phar_f64"][:, :3]).max()
+    assert np.abs(out_phar[0].cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]).max() <= max(10 * ref_err, 1e-4 * scale)
+    # frame 1 is z after the step with s = 6 (executed step index 5), un-normalised
+    ref_z = g["trace_z_f64"][5]
+    got = out_phar[1].cpu().numpy()
+    assert np.abs(got[:, :3] - ref_z[:, :3]).max() <= 1e-4 * max(1.0, np.abs(ref_z[:, :3]).max())
+    assert np.abs(got[:, 3:] - 4.0 * ref_z[:, 3:]).max() <= 1e-4 * max(1.0, np.abs(4 * ref_z[:, 3:]).max())
+
+
+def test_graph_replay_equals_eager_launches():
+    g = load("sampler_ca_small_T20.npz")
+    cfg = case_config("ca_small")
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["pocket_size"])
+    tab = step_table(gamma_table("polynomial_2", 20, 1e-5), 20)
+    h.set_step_table(tab.rows, tab.final)
+    xh = torch.cat([T(g["pocket_x"]), T(g["pocket_one_hot"]).float() / 4], 1).to(DEV)
+    noise = T(g["noise"]).to(DEV)
+    p1 = xh.clone(); out1 = h.sample(p1, noise)
+    n_graph = h.launch_count()
+    h.profile_enable(True)
+    p2 = xh.clone(); out2 = h.sample(p2, noise)
+    ms, n = h.profile_read(0)
+    h.profile_enable(False)
+    assert torch.equal(out1, out2) and torch.equal(p1, p2)
+    assert n == 21 * cfg.n_layers and ms > 0
+    assert h.launch_count() - n_graph == n_graph            # same kernels, launched eagerly
+    p3 = xh.clone(); out3 = h.sample(p3, noise)             # graph again (cached)
+    assert torch.equal(out1, out3)
+
+
+def test_sample_host_equals_device_path():
+    g = load("sampler_ca_small_T20.npz")
+    cfg = case_config("ca_small")
+    h = make_handle(cfg, int(g["wseed"]))
+    h.plan(g["counts"], g["pocket_size"])
+    tab = step_table(gamma_table("polynomial_2", 20, 1e-5), 20)
+    h.set_step_table(tab.rows, tab.final)
+    xh = torch.cat([T(g["pocket_x"]), T(g["pocket_one_hot"]).float() / 4], 1).contiguous()
+    noise = T(g["noise"]).contiguous()
+    out_h = torch.empty(noise.shape[1], 11)
+    pocket_h = torch.empty_like(xh)
+    h.sample_host(xh, noise, out_h, pocket_h)
+    pd = xh.to(DEV).clone()
+    out_d = h.sample(pd, noise.to(DEV))
+    assert torch.equal(out_h, out_d.cpu()) and torch.equal(pocket_h, pd.cpu())
+
+
+def test_full_size_sampler_invariants():
+    """Config-2 size, few steps: COM-free output, rigid pocket, no NaN, no overflow."""
+    cfg = DynamicsConfig()
+    ddpm = build_ddpm(cfg, 0, 500)
+    B, n_res, n_ph = 64, 150, 8
+    pocket = make_pocket_batch([n_res], 20, seed=1, replicate=B)
+    pk = {k: v.to(DEV) for k, v in pocket.items()}
+    torch.manual_seed(0)
+    xh_phar, xh_pocket, mp, mr = ddpm.sample_given_pocket(pk, torch.full((B,), n_ph), timesteps=10)
+    assert torch.isfinite(xh_phar).all()
+    tot = torch.zeros(B, 3, device=DEV).index_add_(0, mp, xh_phar[:, :3])
+    assert tot.abs().max() <= 5e-2
+    assert torch.all(xh_phar[:, 3:].sum(1) == 1)                       # one-hot types
+    x0 = pocket["x"][:n_res]
+    for b in (0, 17, 63):
+        xb = xh_pocket[b * n_res:(b + 1) * n_res, :3].cpu()
+        assert (torch.cdist(xb, xb) - torch.cdist(x0, x0)).abs().max() <= 1e-2
+    assert torch.equal(xh_pocket[:, 3:].cpu(), pocket["one_hot"].float())
