@@ -128,6 +128,7 @@ extern "C" int dp_destroy(dp_handle* h)
     free_bag(h->w.allocations);
     tc_free_weights(h);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     delete h;
     return DP_OK;
 }
@@ -567,9 +568,12 @@ extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float*
             if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
             const int64_t before = h->launches;
             cudaGraph_t g = nullptr;
-            DP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            rc = sampler_step_launches(h, pocket, noise, st);
-            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            // the legacy default stream cannot be captured: record on a handle-owned stream and
+            // replay the instantiated graph on the caller's stream
+            if (!h->capture_stream) DP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+            DP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+            rc = sampler_step_launches(h, pocket, noise, h->capture_stream);
+            cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             DP_CUDA(ce);
             p.graph_launches = h->launches - before;

@@ -179,6 +179,7 @@ struct dp_handle {
     float final_host[4] = {0, 0, 0, 0};
     int n_steps = 0;
     int64_t launches = 0;
+    cudaStream_t capture_stream = nullptr;
     // profiling
     bool profile = false;
     struct Span { int which; cudaEvent_t a, b; };

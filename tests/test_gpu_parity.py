@@ -329,5 +329,6 @@ def test_full_size_sampler_invariants():
     x0 = pocket["x"][:n_res]
     for b in (0, 17, 63):
         xb = xh_pocket[b * n_res:(b + 1) * n_res, :3].cpu()
-        assert (torch.cdist(xb, xb) - torch.cdist(x0, x0)).abs().max() <= 1e-2
+        # rigid translation only: offsets from the first node are preserved
+        assert ((xb - xb[0]) - (x0 - x0[0])).abs().max() <= 2e-3
     assert torch.equal(xh_pocket[:, 3:].cpu(), pocket["one_hot"].float())
