@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 // --------------------------------------------------------------------------------------
 // errors
@@ -105,6 +106,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     h->device = device;
     h->precision = cfg->precision;
     DP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char* m = getenv("DIFFPHAR_TC_MASK")) h->tc_mask = atoi(m);
     int rc = egnn_f32_init();
     if (!rc) rc = tc_init();
     if (rc) { delete h; return rc; }
@@ -206,6 +208,15 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
     if ((rc = lin(W.emb_out, D, H))) return rc;
 
     const int S = c.inv_sublayers, G = c.n_layers * S;
+    // lin_id numbering shared with run_denoiser: GCL i: 4i+0 edge_mlp.2, 4i+1 node_mlp.0, 4i+2 node_mlp.2;
+    // block b: 4G+b coord_mlp.2; projection set v: 4G+L+v
+    h->tc_host.assign((size_t)4 * G + c.n_layers + G + 1, HostLinear());
+    auto reg = [&](int id, const float* w, int out, int in) {       // [out][in] -> k-major copy
+        HostLinear& L = h->tc_host[id];
+        L.K = in; L.n_out = out; L.wt.resize((size_t)in * out);
+        for (int o = 0; o < out; ++o)
+            for (int k = 0; k < in; ++k) L.wt[(size_t)k * out + o] = w[(size_t)o * in + k];
+    };
     W.gcl.resize(G);
     W.coord.resize(c.n_layers);
     std::vector<HostFirstLayer> gcl_first(G), coord_first(c.n_layers);
@@ -222,8 +233,11 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
             gcl_first[b * S + g].w = rd.take((int64_t)H * K1);
             gcl_first[b * S + g].b = rd.take(H);
             if ((rc = scal_cols(gcl_first[b * S + g].w, &L.wr, &L.wd))) return rc;
+            reg(4 * (b * S + g) + 0, rd.p, H, H);
             if ((rc = lin(L.e2, H, H))) return rc;
+            reg(4 * (b * S + g) + 1, rd.p, H, 2 * H);
             if ((rc = lin(L.n0, H, 2 * H))) return rc;
+            reg(4 * (b * S + g) + 2, rd.p, H, H);
             if ((rc = lin(L.n2, H, H))) return rc;
             if (c.attention) {
                 const float* wa = rd.take(H);
@@ -237,6 +251,7 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
         coord_first[b].w = rd.take((int64_t)H * K1);
         coord_first[b].b = rd.take(H);
         if ((rc = scal_cols(coord_first[b].w, &Cw.wr, &Cw.wd))) return rc;
+        reg(4 * G + b, rd.p, H, H);
         if ((rc = lin(Cw.c2, H, H))) return rc;
         const float* w4 = rd.take(H);
         std::vector<float> v(w4, w4 + H);
@@ -269,8 +284,12 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
         }
         if ((rc = upload(bag, &ps.lin.wt, wt))) return rc;
         if ((rc = upload(bag, &ps.lin.b, bias))) return rc;
+        HostLinear& TL = h->tc_host[4 * G + c.n_layers + v];
+        TL.K = H; TL.n_out = n_out; TL.wt = wt;
     }
-    if ((rc = tc_prepare_weights(h, blob))) return rc;
+    if ((rc = tc_prepare_weights(h))) return rc;
+    h->tc_host.clear();
+    h->tc_host.shrink_to_fit();
     h->has_weights = true;
     if (h->plan.step_graph) { cudaGraphExecDestroy(h->plan.step_graph); h->plan.step_graph = nullptr; }
     return DP_OK;
@@ -412,7 +431,7 @@ extern "C" int dp_get_graph(dp_handle* h, const int32_t** rowptr, const int32_t*
 static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st)
 {
     prof_begin(h, PROF_NODE, st);
-    int rc = (h->precision == DP_FP32) ? launch_linear_f32(h, a, st) : launch_linear_tc(h, a, lin_id, st);
+    int rc = (h->precision == DP_FP32 || !(h->tc_mask & 2)) ? launch_linear_f32(h, a, st) : launch_linear_tc(h, a, lin_id, st);
     prof_end(h, st);
     return rc;
 }
@@ -420,7 +439,7 @@ static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_
 static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
 {
     prof_begin(h, a.coord ? PROF_EDGE_COORD : PROF_EDGE_MSG, st);
-    int rc = (h->precision == DP_FP32) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
+    int rc = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
     prof_end(h, st);
     return rc;
 }
@@ -433,7 +452,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
 {
     Plan& p = h->plan; const dp_config& c = h->cfg; DeviceWeights& W = h->w;
     const int S = c.inv_sublayers, G = c.n_layers * S;
-    const int unit = (h->precision == DP_FP32) ? UNIT_F32 : UNIT_TC;
+    const int unit = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? UNIT_F32 : UNIT_TC;
     int rc = 0;
     if ((rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, st))) return rc;
     if ((rc = launch_build_edges(h, p.x_in, st))) return rc;

@@ -115,6 +115,10 @@ struct DeviceWeights {
 };
 
 struct TcWeights;   // tcgen05 operand images (tc_path.cu)
+struct HostLinear {  // k-major fp32 host copy of a linear the tensor-core path packs: wt[k * n_out + o]
+    std::vector<float> wt;
+    int K = 0, n_out = 0;
+};
 
 // ---------------------------------------------------------------------------
 // the plan: batch layout + workspace
@@ -170,9 +174,11 @@ struct dp_handle {
     int device = 0;
     int sm_count = 148;
     int precision = 0;
+    int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
     DeviceWeights w;
     TcWeights* tc = nullptr;
+    std::vector<HostLinear> tc_host;   // indexed by lin_id (see run_denoiser)
     Plan plan;
     bool has_plan = false;
     std::vector<float> step_rows_host;
@@ -245,7 +251,7 @@ int launch_pocket_com_init(dp_handle* h, float* z, const float* pocket, cudaStre
 
 // tc_path.cu (tcgen05)
 int tc_init();
-int tc_prepare_weights(dp_handle* h, const float* blob_host);
+int tc_prepare_weights(dp_handle* h);
 void tc_free_weights(dp_handle* h);
 int launch_linear_tc(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);
 int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);

@@ -108,6 +108,55 @@ def test_dynamics_fp32_vs_reference(name):
     assert h.flags().nan_resets == 0
 
 
+# tensor-core modes: fp16 operands carry TF32's 10-bit mantissa, bf16 8 bits -> tighter bound for f16
+TC_TOL = {"f16": (1e-4, 0.02), "bf16": (1e-3, 0.05)}
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_dynamics_tensor_core_modes_vs_reference(name, prec):
+    g = load(f"dynamics_{name}.npz")
+    cfg = case_config(name)
+    h = make_handle(cfg, int(g["wseed"]), prec)
+    h.plan(g["counts"], g["sizes"])
+    B = len(g["sizes"])
+    xs = max(1.0, float(np.abs(g["z"][:, :3]).max()))
+    tol_h, tol_v = TC_TOL[prec]
+    for i, tv in enumerate(g["t_values"]):
+        out_p, out_r = h.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), torch.full((B,), float(tv)))
+        out_p, out_r = out_p.cpu().numpy(), out_r.cpu().numpy()
+        rp, rr = g[f"eps_phar_f64_{i}"], g[f"eps_res_f64_{i}"]
+        assert np.abs(out_p[:, 3:] - rp[:, 3:]).max() <= tol_h * max(1.0, np.abs(rp[:, 3:]).max())
+        assert np.abs(out_r[:, 3:] - rr[:, 3:]).max() <= tol_h * max(1.0, np.abs(rr[:, 3:]).max())
+        assert np.abs(out_p[:, :3] - rp[:, :3]).max() <= 1e-5 * xs + tol_v * np.abs(rp[:, :3]).max()
+    assert h.flags().nan_resets == 0
+
+
+def test_tensor_core_modes_at_full_size_agree_with_fp32():
+    """config-2 size: every 64-edge tile / 32-edge unit boundary case gets exercised."""
+    cfg = DynamicsConfig()
+    B, n_res, n_ph = 64, 150, 8
+    pocket = make_pocket_batch([n_res], 20, seed=3, replicate=B)
+    gen = torch.Generator().manual_seed(4)
+    com = pocket["x"][:n_res].mean(0)
+    z = torch.cat([com + 5.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(B * n_ph, 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    t = torch.full((B,), 0.4)
+    outs = {}
+    for prec in ("fp32", "f16", "bf16"):
+        h = make_handle(cfg, 0, prec)
+        h.plan([n_ph] * B, [n_res] * B)
+        a, r = h.dynamics_forward(z, xr, t)
+        outs[prec] = (a.cpu(), r.cpu())
+    ref_p, ref_r = outs["fp32"]
+    for prec in ("f16", "bf16"):
+        tol_h, tol_v = TC_TOL[prec]
+        a, r = outs[prec]
+        assert (a[:, 3:] - ref_p[:, 3:]).abs().max() <= tol_h * max(1.0, float(ref_p[:, 3:].abs().max()))
+        assert (r[:, 3:] - ref_r[:, 3:]).abs().max() <= tol_h * max(1.0, float(ref_r[:, 3:].abs().max()))
+        assert (a[:, :3] - ref_p[:, :3]).abs().max() <= 1e-5 * 60 + tol_v * float(ref_p[:, :3].abs().max())
+
+
 def test_dynamics_module_api_and_kwargs():
     from cmd_gen_b200.equivariant_diffusion.dynamics import EGNNDynamics
     g = load("dynamics_ca_small.npz")
@@ -224,15 +273,16 @@ def inject(ddpm, noise):
     ddpm.sample_gaussian = lambda size, device: next(it).to(device)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "f16", "bf16"])
 @pytest.mark.parametrize("fixture,name", [("sampler_ca_small_T500_n12.npz", "ca_small"),
                                           ("sampler_ca_small_T20.npz", "ca_small"),
                                           ("sampler_fa_small_T500_n6.npz", "fa_small")])
-def test_sample_given_pocket_vs_reference(fixture, name):
+def test_sample_given_pocket_vs_reference(fixture, name, prec):
     g = load(fixture)
     cfg = case_config(name)
     Tn = int(g["T"])
     ts = None if int(g["timesteps"]) < 0 else int(g["timesteps"])
-    ddpm = build_ddpm(cfg, int(g["wseed"]), Tn)
+    ddpm = build_ddpm(cfg, int(g["wseed"]), Tn, prec)
     inject(ddpm, T(g["noise"]))
     pocket = {"x": T(g["pocket_x"]).to(DEV), "one_hot": T(g["pocket_one_hot"]).to(DEV),
               "size": T(g["pocket_size"]).to(DEV), "mask": T(g["pocket_mask"]).to(DEV)}
@@ -244,15 +294,19 @@ def test_sample_given_pocket_vs_reference(fixture, name):
     scale = np.abs(g["xh_phar_f64"][:, :3]).max()
     ref_err = np.abs(g["xh_phar_f32"][:, :3] - g["xh_phar_f64"][:, :3]).max()
     err = np.abs(xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]).max()
-    assert err <= max(10 * ref_err, 1e-4 * scale), (err, ref_err, scale)
-    assert np.array_equal(xh_phar.cpu().numpy()[:, 3:], g["xh_phar_f32"][:, 3:])
+    # end-to-end bound: fp32 within 10x the reference's own fp32-vs-fp64 error (or 1e-4 of the scale);
+    # f16 operands 3e-4, bf16 1e-3 of the coordinate scale
+    bound = {"fp32": max(10 * ref_err, 1e-4 * scale), "f16": 3e-4 * scale, "bf16": 1e-3 * scale}[prec]
+    assert err <= bound, (err, ref_err, scale)
+    same = (xh_phar.cpu().numpy()[:, 3:] == g["xh_phar_f32"][:, 3:]).all(1).mean()
+    assert same == 1.0 if prec == "fp32" else same >= 0.9          # type agreement
     perr = np.abs(xh_pocket.cpu().numpy() - g["xh_pocket_f64"]).max()
-    assert perr <= max(10 * ref_err, 1e-4 * scale)
+    assert perr <= bound
     # per-sample RMSD (north_star's end-to-end criterion)
     d = xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]
     for b in np.unique(g["mask_phar"]):
         rmsd = np.sqrt((d[g["mask_phar"] == b] ** 2).sum(1).mean())
-        assert rmsd <= max(10 * ref_err, 1e-4 * scale)
+        assert rmsd <= bound
 
 
 def test_per_step_api_follows_reference_trace():
