@@ -107,6 +107,12 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     h->precision = cfg->precision;
     DP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char* m = getenv("DIFFPHAR_TC_MASK")) h->tc_mask = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_TRACE")) {
+        if (atoi(m)) {
+            DP_CUDA(cudaMalloc(&h->trace, DP_TRACE_WORDS * sizeof(long long)));
+            DP_CUDA(cudaMemset(h->trace, 0, DP_TRACE_WORDS * sizeof(long long)));
+        }
+    }
     int rc = egnn_f32_init();
     if (!rc) rc = tc_init();
     if (rc) { delete h; return rc; }
@@ -131,6 +137,7 @@ extern "C" int dp_destroy(dp_handle* h)
     tc_free_weights(h);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    if (h->trace) cudaFree(h->trace);
     delete h;
     return DP_OK;
 }
@@ -333,6 +340,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
         ecap = (int64_t)((c.edge_cutoff < 0.f || pairs < guess) ? pairs : guess);
     }
     DP_CHECK(ecap < (int64_t)2147483000, DP_ERR_INVALID, "edge capacity %lld exceeds int32 indexing", (long long)ecap);
+    DP_CHECK((int64_t)p.N + 2 * (ecap / UNIT_TC + 2) < (int64_t)2147483000, DP_ERR_INVALID, "batch too large for int32 row indexing");
     p.Ecap = ecap;
     std::vector<int> sample_of(p.N);
     for (int b = 0; b < B; ++b) {
@@ -346,10 +354,11 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
 #define ALLOC(ptr, count) if ((rc = dev_alloc(bag, &(ptr), (size_t)(count)))) return rc
     ALLOC(p.phar_off, B + 1); ALLOC(p.res_off, B + 1); ALLOC(p.sample_of, p.N);
     ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1);
-    ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
+    ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.edst, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
     ALLOC(p.counts, 4);
-    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.agg, (size_t)p.N * H);
-    ALLOC(p.partials, units * 2 * H);
+    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H);
+    ALLOC(p.agg, ((size_t)p.N + units * 2) * H);          // [agg rows | partial rows] contiguous (graph.cu edge_dst)
+    p.partials = p.agg + (size_t)p.N * H;
     ALLOC(p.pq, (size_t)p.N * 4 * H);
     ALLOC(p.x_in, (size_t)p.N * 3); ALLOC(p.x_a, (size_t)p.N * 3); ALLOC(p.x_b, (size_t)p.N * 3);
     ALLOC(p.z, (size_t)p.Np * PW); ALLOC(p.eps_hat, (size_t)p.Np * PW); ALLOC(p.pocket, (size_t)p.Nr * RW);
@@ -478,8 +487,9 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
         e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
+        e.edst = p.edst; e.n_moving = p.Np;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
-        e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh;
+        e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
         // node model: h <- h + W4 silu(W3 [h | agg] + b3) + b4  (egnn_new.py:54-57)
         LinearArgs n0{};
@@ -499,8 +509,9 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
             q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
+            q.edst = p.edst; q.n_moving = p.Np;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
-            q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh;
+            q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
             prof_begin(h, PROF_EDGE_COORD, st);
             rc = launch_coord_finish(h, x_cur, x_next, st);
@@ -683,6 +694,17 @@ extern "C" int dp_reset_flags(dp_handle* h, void* stream)
     DP_CUDA(cudaMemsetAsync(p.counts + 2, 0, sizeof(int), st));
     DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, 2 * sizeof(int), st));
     if (p.stats) DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
+    return DP_OK;
+}
+
+// debug: copies the clock64 timeline the last traced kernel wrote (DIFFPHAR_TRACE=1); not part of the stable ABI
+extern "C" int dp_debug_trace(dp_handle* h, long long* out_host, int32_t n_words)
+{
+    DP_CHECK(h && out_host && n_words > 0 && n_words <= DP_TRACE_WORDS, DP_ERR_INVALID, "dp_debug_trace: bad argument");
+    DP_CHECK(h->trace, DP_ERR_STATE, "tracing is off (set DIFFPHAR_TRACE=1 before dp_create)");
+    DP_CUDA(cudaSetDevice(h->device));
+    DP_CUDA(cudaDeviceSynchronize());
+    DP_CUDA(cudaMemcpy(out_host, h->trace, (size_t)n_words * sizeof(long long), cudaMemcpyDeviceToHost));
     return DP_OK;
 }
 

@@ -9,6 +9,7 @@
 constexpr int H = 256;            // hidden_nf (compile-time tile width)
 constexpr int UNIT_F32 = 64;      // edges per segmented-sum unit, FFMA path
 constexpr int UNIT_TC = 32;       // edges per segmented-sum unit, tcgen05 path
+constexpr int DP_TRACE_WORDS = 3 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
 
 void dp_set_error(const char* fmt, ...);
 
@@ -136,6 +137,7 @@ struct Plan {
     int* rowptr = nullptr;       // [N+1]
     int* col = nullptr;          // [Ecap]
     int* erow = nullptr;         // [Ecap]
+    int* edst = nullptr;         // [Ecap] segmented-sum destination per edge for 32-edge units (see graph.cu)
     float* d0 = nullptr;         // [Ecap] squared input-frame distances (edge_attr, egnn_new.py:195)
     int* counts = nullptr;       // [4]: E, E_p, overflow, spare
     // node state
@@ -186,6 +188,7 @@ struct dp_handle {
     int n_steps = 0;
     int64_t launches = 0;
     cudaStream_t capture_stream = nullptr;
+    long long* trace = nullptr;        // debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernels (DIFFPHAR_TRACE=1)
     // profiling
     bool profile = false;
     struct Span { int which; cudaEvent_t a, b; };
@@ -222,10 +225,13 @@ struct EdgeArgs {
     const float* wv; float bv;                       // final vector: attention / coord_mlp.4
     const float* x;                                  // current coordinates [N][3]
     const float* d0; const int* erow; const int* ecol; const int* rowptr;
+    const int* edst;                                 // per-edge segmented-sum destination (graph.cu), tcgen05 path
+    int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)
     int coord; int attention; int use_tanh;
+    long long* trace;                                // debug timeline (dp_debug_trace), normally null
 };
 int launch_edge_f32(dp_handle* h, const EdgeArgs& a, cudaStream_t st);
 int egnn_f32_init();
@@ -254,7 +260,8 @@ int tc_init();
 int tc_prepare_weights(dp_handle* h);
 void tc_free_weights(dp_handle* h);
 int launch_linear_tc(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);
-int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);
+int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);   // tc_edge.cu
+int tc_edge_init();
 
 // api.cu helpers
 void prof_begin(dp_handle* h, int which, cudaStream_t st);

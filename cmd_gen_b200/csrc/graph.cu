@@ -21,7 +21,7 @@ struct GraphArgs {
     float cutoff;          // < 0: none
     int* deg;
     const int* rowptr;
-    int* col; int* erow; float* d0;
+    int* col; int* erow; float* d0; int* edst;
     int* counts;           // [0]=E [1]=E_p [2]=overflow
     long long ecap;
 };
@@ -30,6 +30,19 @@ __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float
 {
     const float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj), dz = __fsub_rn(zi, zj);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Where the tcgen05 edge kernel's epilogue stores the running sum after edge `pos` (32-edge units,
+// UNIT_TC), as a row of the contiguous [agg (N rows) | partials (2 per unit)] buffer: -1 = keep
+// accumulating; the row lies inside one unit -> agg row; the row crosses a unit boundary -> partial row
+// N + 2 unit + slot (slot 0: the segment containing the unit's first edge).
+__device__ __forceinline__ int edge_dst(int n_nodes, int row, long long rs, long long re, long long pos)
+{
+    const bool is_end = (pos == re - 1) || ((pos & (UNIT_TC - 1)) == UNIT_TC - 1);
+    if (!is_end) return -1;
+    const long long u0 = pos & ~(long long)(UNIT_TC - 1);
+    if (rs >= u0 && re <= u0 + UNIT_TC) return row;
+    return n_nodes + (int)((pos / UNIT_TC) * 2 + (rs <= u0 ? 0 : 1));
 }
 
 // FILL = false: count neighbours into deg[]; FILL = true: write col/erow/d0 at rowptr[row].
@@ -46,6 +59,7 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
         const int hi[2] = {a.phar_off[b + 1], a.Np + a.res_off[b + 1]};
         int found = 0;
         long long base = FILL ? (long long)a.rowptr[row] : 0;
+        const long long row_end = FILL ? (long long)a.rowptr[row + 1] : 0;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
             for (int j0 = lo[part]; j0 < hi[part]; j0 += 32) {
@@ -63,6 +77,7 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
                         a.col[pos] = j;
                         a.erow[pos] = row;
                         a.d0[pos] = d2;
+                        a.edst[pos] = edge_dst(a.N, row, base, row_end, pos);
                     }
                 }
                 found += __popc(m);
@@ -127,7 +142,7 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     GraphArgs a;
     a.x = x_dev; a.sample_of = p.sample_of; a.phar_off = p.phar_off; a.res_off = p.res_off;
     a.N = p.N; a.Np = p.Np; a.cutoff = h->cfg.edge_cutoff;
-    a.deg = p.deg; a.rowptr = p.rowptr; a.col = p.col; a.erow = p.erow; a.d0 = p.d0;
+    a.deg = p.deg; a.rowptr = p.rowptr; a.col = p.col; a.erow = p.erow; a.d0 = p.d0; a.edst = p.edst;
     a.counts = p.counts; a.ecap = p.Ecap;
     const int wpb = 8;
     int grid = (p.N + wpb - 1) / wpb;

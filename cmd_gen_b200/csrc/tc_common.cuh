@@ -1,0 +1,198 @@
+// PTX wrappers and operand-layout helpers shared by the tcgen05 kernels (tc_edge.cu, tc_node.cu).
+//
+// Operand layout: canonical K-major SWIZZLE_128B — rows of 128 bytes (64 16-bit K elements = one
+// "panel"), 8-row atoms of 1024 B, the 16-byte chunk index XORed with (row % 8).  Weights are
+// pre-swizzled on the host into exactly that image (tc_weights.cu) and arrive with cp.async.bulk
+// (TMA engine, SASS UBLKCP) + mbarrier complete_tx; activation tiles are produced by CUDA cores
+// straight into the same layout and handed to the async proxy with fence.proxy.async.
+#pragma once
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace tc {
+
+constexpr int FMT_F16 = 0, FMT_BF16 = 1;
+constexpr int PANEL_K = 64;                 // 16-bit elements per 128-byte swizzle row
+constexpr int W_PANEL_BYTES = 256 * 128;    // 256 out channels x 128 B (one K panel of a 256-channel block)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- bulk copy global -> shared (TMA engine, 1-D) ---------------------------------------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- TMEM ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(holder_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    tmem_ld32_issue(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt | bit 15/16 A/B major
+// (0 = K) | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N)
+{
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- numerics -----------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi)
+{
+    if (FMT == FMT_BF16) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&t);
+    } else {
+        __half2 t = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
+}
+__device__ __forceinline__ float tanh_approx(float v)
+{
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float v)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// SiLU(v) = v * sigmoid(v).
+//   FMT_BF16: 0.5 v (1 + tanh(0.5 v)) — ONE MUFU op (tanh.approx.f32, rel. error 2^-11, far inside
+//             bf16's 2^-9 operand rounding) + 2 FMA-pipe ops.  The MUFU pipe (16 lanes/clk/SM) is the
+//             scarcest resource of the edge kernel: two SiLUs per edge-channel.
+//   FMT_F16 : v * rcp(1 + 2^(-v log2 e)) — two MUFU ops, ~1e-7 relative: the accurate mode keeps
+//             its error budget for the fp16 operand rounding.
+template <int FMT>
+__device__ __forceinline__ float silu_tc(float v)
+{
+    if (FMT == FMT_BF16) {
+        const float hv = 0.5f * v;
+        return fmaf(hv, tanh_approx(hv), hv);
+    } else {
+        return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v));
+    }
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
+
+// byte offset of the 16-byte chunk `chunk` (8 consecutive K elements) of item `i` inside a swizzled
+// activation tile whose K panels are `panel_bytes` apart (panel_bytes = items * 128)
+__device__ __forceinline__ uint32_t chunk_offset(int i, int chunk, int panel_bytes)
+{
+    return (uint32_t)((chunk >> 3) * panel_bytes + i * 128 + (((chunk & 7) ^ (i & 7)) << 4));
+}
+
+}  // namespace tc
+
+// ---- weight images (tc_weights.cu) ----------------------------------------------------------------
+struct TcLinearImg { unsigned char* img[2] = {nullptr, nullptr}; int K = 0, n_out = 0; };
+struct TcNodeImg {                     // concatenated panel stream of one fused node-phase launch
+    unsigned char* img[2] = {nullptr, nullptr};
+    int n_panels = 0;
+};
+struct TcWeights {
+    std::vector<TcLinearImg> lin;      // indexed by lin_id (see run_denoiser)
+    std::vector<TcNodeImg> node;       // indexed by h version v = 0..G
+    std::vector<void*> allocations;
+};
+int tc_fmt_of(dp_handle* h, int* fmt);

@@ -1,0 +1,374 @@
+// K2 / K3 — the fused edge kernel on the 5th-generation tensor cores (DP_BF16 / DP_F16).
+//
+//   message mode : GCL.edge_model + attention gate + CSR segmented sum   (egnn_new.py:31-52, 276-285)
+//   coord mode   : EquivariantUpdate.coord_mlp up to its per-edge scalar  (egnn_new.py:87-91)
+//
+// Per 64-edge tile:   X = SiLU(Pa[row] + Pb[col] + r2 wr + d0 wd)            first layer (factored: the two
+//                                                                            H x H products are per NODE, tc_path.cu)
+//                     D[256 ch, 64 edges] = W2[256, 256] . X^T              tcgen05.mma, fp32 accumulators in TMEM
+//                     m = SiLU(D + b2);  g = sigmoid(wa . m + ba);  agg[row] += g m
+//
+// Orientation ("channels on lanes"): A = the nn.Linear weight exactly as stored ([out,in] row-major ==
+// K-major), B = the activation tile.  The accumulator has the OUTPUT CHANNEL on the TMEM lane and the
+// edges along TMEM columns, so the CSR segmented sum is a run of register FMAs inside one thread —
+// no atomics, no shuffles — and agg stores are 128 B coalesced.
+//
+// Warp-specialised, persistent (one CTA per SM, tiles round-robin):
+//   warps 0-7   epilogue : TMEM -> registers, SiLU, gate (smem-transposed reduce over the 256 channels),
+//                          segmented sum, stores.  warp w reads TMEM lanes 32 (w % 4) .. +32.
+//   warps 8-15  producer : each warp owns 8 edges of the tile: gathers the pre-projected rows (Pa once per
+//                          CSR row run, Pb per edge; 128-bit loads, 8 in flight per lane), first layer,
+//                          writes the swizzled K-major B tile, fence.proxy.async, arrives on full[stage].
+//   warp  16    MMA      : (warps 17-19 idle: they only donate their registers, setmaxnreg) one thread waits full[stage] / tmem_empty[acc], issues 32 tcgen05.mma
+//                          (M=128, N=64, K=16) per tile and commits to x_empty[stage] + tmem_full[acc].
+// Second-layer weights (128 KB swizzled bf16/f16 image) stay resident in shared memory for the whole
+// kernel, fetched once per CTA with cp.async.bulk.  2 activation stages x 32 KB, 4 accumulator stages
+// x 128 TMEM columns.
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int TILE = 64;                          // edges per tile (UMMA N)
+constexpr int X_PANEL_BYTES = TILE * 128;         // 8 KB
+constexpr int X_TILE_BYTES = 4 * X_PANEL_BYTES;   // 32 KB: 64 edges x 256 K x 2 B
+constexpr int N_XS = 2;                           // activation stages
+constexpr int N_TS = 4;                           // accumulator stages
+constexpr int TS_COLS = 2 * TILE;                 // TMEM columns per accumulator stage
+constexpr int EPI_WARPS = 8, PRO_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS + PRO_WARPS;
+constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 5 warpgroups: 2 epilogue, 2 producer, 1 MMA (+3 idle warps)
+// Registers are allocated per SM sub-partition (16384 each, 5 warps per sub-partition here), so the launch
+// gets 96 per thread; setmaxnreg then moves the idle warpgroup's share to the producers.
+constexpr int REGS_MMA = 40, REGS_PRODUCER = 120;
+constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer
+
+struct EdgeSmem {                                 // offsets from a 1024-aligned base
+    unsigned char w[4 * W_PANEL_BYTES];           // 128 KB resident second-layer weights
+    unsigned char x[N_XS][X_TILE_BYTES];          // 64 KB
+    float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel][16 edges (+4 pad)]
+    float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over units
+    float gate[EPI_WARPS][32];
+    unsigned long long bar_w;
+    unsigned long long bar_full[N_XS], bar_xempty[N_XS];
+    unsigned long long bar_tfull[N_TS], bar_tempty[N_TS];
+    uint32_t tmem_holder;
+};
+
+// D[256 x 64] = W[256 x 256] * X[64 x 256]^T  as 2 (M halves) x 4 (panels) x 4 (K steps) MMAs
+__device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t w_base, uint32_t x_base, uint32_t idesc)
+{
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+        for (int ks = 0; ks < PANEL_K / 16; ++ks) {
+            const uint64_t bdesc = make_desc(x_base + kp * X_PANEL_BYTES + ks * 32);
+            const uint32_t acc = (kp > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint64_t adesc = make_desc(w_base + kp * W_PANEL_BYTES + hh * (128 * 128) + ks * 32);
+                umma_f16(tmem_d + hh * TILE, adesc, bdesc, idesc, acc);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void unpack8(const float4& a, const float4& b, float (&v)[8])
+{
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// debug timeline: role 0 = producer warp 0, 1 = MMA thread, 2 = epilogue warp 0; CTA 0 only
+__device__ __forceinline__ void trace_mark(long long* trace, int role, int it, int slot)
+{
+    if (trace && blockIdx.x == 0 && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64();
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const unsigned char* __restrict__ w_img)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    EdgeSmem& s = *reinterpret_cast<EdgeSmem*>(base);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int E = *a.n_edges;
+    const int n_tiles = (E + TILE - 1) / TILE;
+    if ((int)blockIdx.x >= n_tiles) return;           // uniform per CTA, before any barrier / allocation
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&s.bar_w), 1);
+        for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
+        for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), N_TS * TS_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_holder;
+
+    if (wid >= MMA_WARP) {
+        // ================================ MMA issuer ================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+        if (wid == MMA_WARP && lane == 0) {
+            const uint32_t bar_w = smem_u32(&s.bar_w);
+            mbar_expect_tx(bar_w, 4 * W_PANEL_BYTES);
+            for (int p = 0; p < 4; ++p)
+                bulk_g2s(smem_u32(s.w + p * W_PANEL_BYTES), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, bar_w);
+            constexpr uint32_t idesc = make_idesc(FMT, 128, TILE);
+            trace_mark(a.trace, 1, 63, 0);
+            mbar_wait(bar_w, 0);
+            trace_mark(a.trace, 1, 63, 1);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int xs = it % N_XS, ts = it % N_TS;
+                trace_mark(a.trace, 1, it, 0);
+                mbar_wait(smem_u32(&s.bar_full[xs]), (it / N_XS) & 1);
+                trace_mark(a.trace, 1, it, 1);
+                mbar_wait(smem_u32(&s.bar_tempty[ts]), ((it / N_TS) & 1) ^ 1);
+                trace_mark(a.trace, 1, it, 2);
+                tc_fence_after();
+                issue_tile_mma(tmem_base + ts * TS_COLS, smem_u32(s.w), smem_u32(s.x[xs]), idesc);
+                umma_commit(smem_u32(&s.bar_xempty[xs]));
+                umma_commit(smem_u32(&s.bar_tfull[ts]));
+                trace_mark(a.trace, 1, it, 3);
+            }
+        }
+    } else if (wid >= EPI_WARPS) {
+        // ================================ producer ================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        const int pw = wid - EPI_WARPS;
+        float wr[8], wd[8];
+        unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
+        unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
+        const float* pa_base = a.p + a.off_a + 8 * lane;
+        const float* pb_base = a.p + a.off_b + 8 * lane;
+
+        // metadata of the warp's 8 edges lives on lanes 0-7 and is software-pipelined one tile ahead:
+        //   (1) top of tile t: issue the (row, col, d0) loads of tile t+1
+        //   (2) after the first half of tile t: their results have landed -> issue the x loads of moved endpoints
+        //   (3) end of tile t: squared distance in the current frame (coord2diff, egnn_new.py:265-268)
+        int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f; bool m_valid = false;
+        auto load_rc = [&](int it, int& r, int& c, float& d0, bool& valid) {
+            const int e = (blockIdx.x + it * gridDim.x) * TILE + 8 * pw + lane;
+            valid = (it < my_tiles) && lane < 8 && e < E;
+            r = 0; c = 0; d0 = 0.f;
+            if (valid) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
+        };
+        auto dist2 = [&](int r, int c) {
+            const float dx = a.x[3 * r] - a.x[3 * c], dy = a.x[3 * r + 1] - a.x[3 * c + 1], dz = a.x[3 * r + 2] - a.x[3 * c + 2];
+            return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        };
+        load_rc(0, m_row, m_col, m_d0, m_valid);
+        m_r2 = m_d0;
+        if (m_valid && (m_row < a.n_moving || m_col < a.n_moving)) m_r2 = dist2(m_row, m_col);
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const int xs = it % N_XS;
+            int n_row, n_col; float n_d0, n_r2; bool n_valid;
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 0);
+            load_rc(it + 1, n_row, n_col, n_d0, n_valid);                               // (1)
+            mbar_wait(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
+            unsigned char* xt = s.x[xs];
+            float cur[8];                                                                // Pa chunk of the current row run
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = 0.f;
+            int prev_row = -1;
+            float xr0 = 0.f, xr1 = 0.f, xr2 = 0.f, xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
+            bool n_moving = false;
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                float4 pa[4][2], pb[4][2];
+                int rows[4]; bool fresh[4], ok[4]; float r2v[4], d0v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 4 * hb + u;
+                    rows[u] = __shfl_sync(0xffffffffu, m_row, i);
+                    const int c = __shfl_sync(0xffffffffu, m_col, i);
+                    ok[u] = __shfl_sync(0xffffffffu, (int)m_valid, i) != 0;
+                    r2v[u] = __shfl_sync(0xffffffffu, m_r2, i);
+                    d0v[u] = __shfl_sync(0xffffffffu, m_d0, i);
+                    fresh[u] = ok[u] && rows[u] != prev_row;
+                    if (ok[u]) {
+                        const float* rb = pb_base + (size_t)c * a.ldp;
+                        pb[u][0] = *reinterpret_cast<const float4*>(rb); pb[u][1] = *reinterpret_cast<const float4*>(rb + 4);
+                        prev_row = rows[u];
+                    }
+                    if (fresh[u]) {
+                        const float* ra = pa_base + (size_t)rows[u] * a.ldp;
+                        pa[u][0] = *reinterpret_cast<const float4*>(ra); pa[u][1] = *reinterpret_cast<const float4*>(ra + 4);
+                    }
+                }
+                if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2 + 2 * hb);
+                if (hb == 1) {                                                          // (2)
+                    n_moving = n_valid && (n_row < a.n_moving || n_col < a.n_moving);
+                    if (n_moving) {
+                        xr0 = a.x[3 * n_row]; xr1 = a.x[3 * n_row + 1]; xr2 = a.x[3 * n_row + 2];
+                        xc0 = a.x[3 * n_col]; xc1 = a.x[3 * n_col + 1]; xc2 = a.x[3 * n_col + 2];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 8 * pw + 4 * hb + u;                                   // edge index inside the tile
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (fresh[u]) unpack8(pa[u][0], pa[u][1], cur);
+                    if (ok[u]) {
+                        float vb[8], y[8];
+                        unpack8(pb[u][0], pb[u][1], vb);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            y[k] = silu_tc<FMT>(fmaf(d0v[u], wd[k], fmaf(r2v[u], wr[k], cur[k] + vb[k])));
+                        o = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+                    }
+                    *reinterpret_cast<uint4*>(xt + chunk_offset(i, lane, X_PANEL_BYTES)) = o;
+                }
+                if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 3 + 2 * hb);
+            }
+            fence_proxy_async();                                                        // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.bar_full[xs]));
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 6);
+            n_r2 = n_d0;                                                                // (3)
+            if (n_moving) {
+                const float dx = xr0 - xc0, dy = xr1 - xc1, dz = xr2 - xc2;
+                n_r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            }
+            m_row = n_row; m_col = n_col; m_d0 = n_d0; m_r2 = n_r2; m_valid = n_valid;
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int ew = wid, q = ew & 3, half = ew >> 2;
+        const int ch = 128 * half + 32 * q + lane;
+        const float b2c = a.b2[ch];
+        const bool gated = a.coord || a.attention;
+        const float wvc = gated ? a.wv[ch] : 0.f;
+        static_assert(H == 256, "segment stores shift by 8");
+        float* out_ch = a.agg + ch;                                                      // [agg rows | partial rows], see graph.cu edge_dst
+        float* redw = s.red[ew];
+        const int g = lane >> 4, l16 = lane & 15;
+        int unit_no = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int ts = it % N_TS;
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int e0 = tile * TILE;
+            const int dst0 = (!a.coord && e0 + lane < E) ? a.edst[e0 + lane] : -1;
+            const int dst1 = (!a.coord && e0 + 32 + lane < E) ? a.edst[e0 + 32 + lane] : -1;
+            if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 0);
+            mbar_wait(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
+            tc_fence_after();
+            if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 1);
+#pragma unroll 1
+            for (int un = 0; un < 2; ++un, ++unit_no) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + ts * TS_COLS + half * TILE + un * 32, v);
+                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 2 + 7 * un);
+                if (un == 1) {                                                          // accumulator stage drained
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = silu_tc<FMT>(v[j] + b2c);
+                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 3 + 7 * un);
+                const int u0 = e0 + 32 * un;                                             // first edge of this 32-edge unit
+                float gate = 1.f;
+                if (gated) {
+                    // sum over the 256 channels of wv[c] * m[c, edge]: per warp a transposed reduce through
+                    // shared memory (thread = channel writes rows, thread = edge sums columns), then 8 warps
+                    float tot2[2];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int j = 16 * hh + 4 * j4;
+                            *reinterpret_cast<float4*>(redw + lane * RED_STRIDE + 4 * j4) =
+                                make_float4(wvc * v[j], wvc * v[j + 1], wvc * v[j + 2], wvc * v[j + 3]);
+                        }
+                        __syncwarp();
+                        float t = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < 16; ++kk) {
+                            const int k = (kk & 3) + 8 * (kk >> 2) + 4 * g;              // bank-conflict-free split of the 32 channels
+                            t += redw[k * RED_STRIDE + l16];
+                        }
+                        t += __shfl_xor_sync(0xffffffffu, t, 16);
+                        tot2[hh] = t;
+                        __syncwarp();
+                    }
+                    const int pbuf = unit_no & 1;
+                    s.part[pbuf][ew][lane] = g ? tot2[1] : tot2[0];                      // lane = edge inside the unit
+                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 4 + 7 * un);
+                    named_bar_sync(1, EPI_WARPS * 32);
+                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 5 + 7 * un);
+                    float tot = a.bv;
+#pragma unroll
+                    for (int k = 0; k < EPI_WARPS; ++k) tot += s.part[pbuf][k][lane];
+                    if (a.coord) gate = a.use_tanh ? tanhf(tot) : tot;                   // egnn_new.py:90-93
+                    else gate = sigmoid_fast(tot);                                       // egnn_new.py:26-29
+                }
+                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 6 + 7 * un);
+                if (a.coord) {
+                    if (ew == 0 && u0 + lane < E) a.escal[u0 + lane] = gate;
+                } else {
+                    // segmented sum over this unit's edges: thread = channel, registers = edges
+                    float gj[32];
+                    if (gated) {
+                        s.gate[ew][lane] = gate;
+                        __syncwarp();
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 t = *reinterpret_cast<const float4*>(&s.gate[ew][4 * j4]);
+                            gj[4 * j4] = t.x; gj[4 * j4 + 1] = t.y; gj[4 * j4 + 2] = t.z; gj[4 * j4 + 3] = t.w;
+                        }
+                        __syncwarp();
+                    }
+                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 7 + 7 * un);
+                    const int my_dst = un ? dst1 : dst0;
+                    const unsigned last_mask = __ballot_sync(0xffffffffu, my_dst >= 0);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        sum = gated ? fmaf(gj[j], v[j], sum) : sum + v[j];
+                        if (last_mask & (1u << j)) {                                     // warp-uniform
+                            const unsigned d = (unsigned)__shfl_sync(0xffffffffu, my_dst, j);
+                            out_ch[(size_t)d << 8] = sum;                                // row d of [agg | partials], H = 256
+                            sum = 0.f;
+                        }
+                    }
+                }
+                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 8 + 7 * un);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == MMA_WARP) tmem_dealloc(tmem_base, N_TS * TS_COLS);
+}
+
+}  // namespace
+
+int tc_edge_init()
+{
+    static_assert(sizeof(EdgeSmem) + 1024 <= 232448, "edge kernel shared memory exceeds 227 KB");
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem) + 1024));
+    return DP_OK;
+}
+
+int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
+{
+    int fmt = 0, rc = tc_fmt_of(h, &fmt);
+    if (rc) return rc;
+    DP_CHECK(h->tc && lin_id >= 0 && lin_id < (int)h->tc->lin.size() && h->tc->lin[lin_id].img[fmt], DP_ERR_STATE,
+             "tc edge layer %d has no weight image", lin_id);
+    const TcLinearImg& L = h->tc->lin[lin_id];
+    DP_CHECK(L.K == H && L.n_out == H, DP_ERR_INVALID, "tc edge layer %d: shape mismatch", lin_id);
+    const int smem = (int)sizeof(EdgeSmem) + 1024;
+    const int grid = h->sm_count;
+    if (fmt == tc::FMT_BF16) edge_tc_kernel<tc::FMT_BF16><<<grid, THREADS, smem, st>>>(a, L.img[fmt]);
+    else edge_tc_kernel<tc::FMT_F16><<<grid, THREADS, smem, st>>>(a, L.img[fmt]);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}

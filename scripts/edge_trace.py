@@ -1,0 +1,49 @@
+"""GPU debug tool: per-role clock64 timeline of CTA 0 of the tcgen05 edge kernel (last message-kernel launch
+of one denoiser evaluation at config-2 size).  DIFFPHAR_TRACE=1 python scripts/edge_trace.py [precision]"""
+import ctypes as C
+import os
+import sys
+
+os.environ["DIFFPHAR_TRACE"] = "1"
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cmd_gen_b200 import _lib
+from cmd_gen_b200.config import DynamicsConfig
+from cmd_gen_b200.synthetic import make_pocket_batch
+from cmd_gen_b200.weights import init_weights, pack_blob
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+cfg = DynamicsConfig()
+B, n_res, n_ph = 64, 150, 8
+h = _lib.Handle(cfg, "cuda:0", prec)
+h.set_weights(pack_blob(cfg, init_weights(cfg, 0)))
+pocket = make_pocket_batch([n_res], 20, seed=3, replicate=B)
+gen = torch.Generator().manual_seed(4)
+com = pocket["x"][:n_res].mean(0)
+z = torch.cat([com + 5.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(B * n_ph, 8, generator=gen)], 1)
+xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+h.plan([n_ph] * B, [n_res] * B)
+t = torch.full((B,), 0.4)
+for _ in range(3):
+    h.dynamics_forward(z, xr, t)
+torch.cuda.synchronize()
+n = 3 * 64 * 16
+buf = (C.c_longlong * n)()
+h.lib.dp_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+rc = h.lib.dp_debug_trace(h.h, buf, n)
+assert rc == 0, h.lib.dp_last_error()
+tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(3)]
+t0 = min(v for r in tr for it in r for v in it if v > 0)
+names = {0: ["start", "xempty", "b0 issued", "b0 done", "b1 issued", "b1 done", "arrive"],
+         1: ["start", "full", "tempty", "issued"],
+         2: ["start", "tfull", "ld0", "silu0", "red0", "bar0", "gate0", "bcast0", "seg0",
+             "ld1", "silu1", "red1", "bar1", "gate1", "bcast1", "seg1"]}
+print("E =", h.flags().last_n_edges, " (cycles relative to the first mark, CTA 0)")
+w = tr[1][63]
+print(f"weights: issue {w[0] - t0}  landed {w[1] - t0}")
+for it in range(10):
+    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue")):
+        row = tr[r][it]
+        if not any(row):
+            continue
+        print(f"it {it} {rn:9s} " + "  ".join(f"{nm}={row[k] - t0}" for k, nm in enumerate(names[r]) if row[k]))
