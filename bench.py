@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DIFFPHAR_PRECISION", "fp32"),
+    ap.add_argument("--precision", default=os.environ.get("DIFFPHAR_PRECISION", "bf16"),
                     choices=["fp32", "tf32", "bf16", "f16"])
     ap.add_argument("--timesteps", type=int, default=WORKLOAD["T"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -109,6 +109,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_TC_MASK")) h->tc_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
+            h->trace_kernel = atoi(m);
             DP_CUDA(cudaMalloc(&h->trace, DP_TRACE_WORDS * sizeof(long long)));
             DP_CUDA(cudaMemset(h->trace, 0, DP_TRACE_WORDS * sizeof(long long)));
         }
@@ -479,7 +480,14 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     av.agg = p.agg; av.partials = p.partials; av.rowptr = p.rowptr; av.unit = unit;
     av.norm = c.normalization_factor; av.inv_norm = 1.0f / c.normalization_factor; av.mean = c.aggregation_mean;
 
-    if ((rc = project(0))) return rc;
+    const bool fused_node = h->precision != DP_FP32 && (h->tc_mask & 2);
+    auto node_phase = [&](int v) -> int {      // tcgen05: node MLP of GCL v-1 + projection of the new h, one launch
+        prof_begin(h, PROF_NODE, st);
+        int e = launch_node_tc(h, v, av, st);
+        prof_end(h, st);
+        return e;
+    };
+    if ((rc = fused_node ? node_phase(0) : project(0))) return rc;
     for (int i = 0; i < G; ++i) {
         const GclWeights& L = W.gcl[i];
         const ProjSet& pin = W.proj[i];
@@ -489,9 +497,12 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
         e.edst = p.edst; e.n_moving = p.Np;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
-        e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace;
+        e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
         // node model: h <- h + W4 silu(W3 [h | agg] + b3) + b4  (egnn_new.py:54-57)
+        if (fused_node) {
+            if ((rc = node_phase(i + 1))) return rc;
+        } else {
         LinearArgs n0{};
         n0.x = p.h; n0.ldx = H; n0.two_source = 1; n0.aggv = av; n0.n_rows = p.N; n0.K = 2 * H;
         n0.wt = L.n0.wt; n0.bias = L.n0.b; n0.n_out = H; n0.y = p.tbuf; n0.ldy = H; n0.epi = 1;
@@ -501,6 +512,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         n2.wt = L.n2.wt; n2.bias = L.n2.b; n2.n_out = H; n2.y = p.h; n2.ldy = H; n2.resid = p.h; n2.ldr = H; n2.epi = 2;
         if ((rc = run_linear(h, n2, 4 * i + 2, st))) return rc;
         if ((rc = project(i + 1))) return rc;
+        }
         if ((i + 1) % S == 0) {
             const int b = i / S;
             const CoordWeights& Cw = W.coord[b];

@@ -188,6 +188,7 @@ struct dp_handle {
     int n_steps = 0;
     int64_t launches = 0;
     cudaStream_t capture_stream = nullptr;
+    int trace_kernel = 0;              // DIFFPHAR_TRACE: 1 = node kernel, 2 = edge message kernel
     long long* trace = nullptr;        // debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernels (DIFFPHAR_TRACE=1)
     // profiling
     bool profile = false;
@@ -262,6 +263,8 @@ void tc_free_weights(dp_handle* h);
 int launch_linear_tc(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);
 int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);   // tc_edge.cu
 int tc_edge_init();
+int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st);                 // tc_node.cu
+int tc_node_init();
 
 // api.cu helpers
 void prof_begin(dp_handle* h, int which, cudaStream_t st);

@@ -19,49 +19,60 @@ struct EncodeArgs {
     const float *re0w, *re0b, *re2w, *re2b;
     const float *embw, *embb;                         // [D][H], [H]
     float* h; float* x_in; float* x_a; float* x_b;
+    int* nan_flag;                                    // [0] cleared here: first kernel of every denoiser evaluation
 };
+
+// One warp per node.  Every layer is out[o] = b[o] + sum_k in[k] w[k][o] with the outputs spread over
+// lanes (o = lane + 32 m: coalesced weight reads, weights stay L1-resident) and the inputs broadcast by
+// shuffle from the lanes that hold them.  Accumulation order = ascending k, like the reference's addmm.
+template <int MAX_OUT32>
+__device__ __forceinline__ void warp_linear(const float (&in)[4], int K, const float* __restrict__ w, const float* __restrict__ b,
+                                            int n_out, int lane, float (&out)[MAX_OUT32])
+{
+#pragma unroll
+    for (int m = 0; m < MAX_OUT32; ++m) out[m] = (lane + 32 * m < n_out) ? b[lane + 32 * m] : 0.f;
+    for (int k = 0; k < K; ++k) {
+        const int src = k & 31, reg = k >> 5;
+        const float v = __shfl_sync(0xffffffffu, reg == 0 ? in[0] : reg == 1 ? in[1] : reg == 2 ? in[2] : in[3], src);
+        const float* wr = w + (size_t)k * n_out;
+#pragma unroll
+        for (int m = 0; m < MAX_OUT32; ++m)
+            if (lane + 32 * m < n_out) out[m] = fmaf(v, wr[lane + 32 * m], out[m]);
+    }
+}
 
 __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
 {
-    __shared__ float feat[64];     // raw type features (<= 64)
-    __shared__ float hid[128];     // 2 * nf hidden
-    __shared__ float joint[72];    // J (+1 time)
-    const int tid = threadIdx.x;
-    for (int node = blockIdx.x; node < a.N; node += gridDim.x) {
-        const bool phar = node < a.Np;
-        const int nf = phar ? a.P : a.R;
-        const float* src = phar ? a.xh_phar + (size_t)node * (3 + a.P) : a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
-        const float *w0 = phar ? a.pe0w : a.re0w, *b0 = phar ? a.pe0b : a.re0b;
-        const float *w2 = phar ? a.pe2w : a.re2w, *b2 = phar ? a.pe2b : a.re2b;
-        if (tid < nf) feat[tid] = src[3 + tid];
-        if (tid < 3) {
-            const float v = src[tid];
-            a.x_in[3 * node + tid] = v; a.x_a[3 * node + tid] = v; a.x_b[3 * node + tid] = v;
-        }
-        __syncthreads();
-        if (tid < 2 * nf) {
-            float acc = b0[tid];
-            for (int k = 0; k < nf; ++k) acc = fmaf(feat[k], w0[k * 2 * nf + tid], acc);
-            hid[tid] = silu_f(acc);
-        }
-        __syncthreads();
-        if (tid < a.J) {
-            float acc = b2[tid];
-            for (int k = 0; k < 2 * nf; ++k) acc = fmaf(hid[k], w2[k * a.J + tid], acc);
-            joint[tid] = acc;
-        }
-        if (tid == 0 && a.D > a.J) {
-            const int step = a.step_idx ? *a.step_idx : 0;
-            joint[a.J] = a.t_base[(size_t)step * a.row_stride + (size_t)a.sample_of[node] * a.t_stride];
-        }
-        __syncthreads();
-        {
-            float acc = a.embb[tid];
-            for (int k = 0; k < a.D; ++k) acc = fmaf(joint[k], a.embw[k * H + tid], acc);
-            a.h[(size_t)node * H + tid] = acc;
-        }
-        __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.nan_flag[0] = 0;
+    if (node >= a.N) return;
+    const bool phar = node < a.Np;
+    const int nf = phar ? a.P : a.R;
+    const float* src = phar ? a.xh_phar + (size_t)node * (3 + a.P) : a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
+    const float *w0 = phar ? a.pe0w : a.re0w, *b0 = phar ? a.pe0b : a.re0b;
+    const float *w2 = phar ? a.pe2w : a.re2w, *b2 = phar ? a.pe2b : a.re2b;
+    if (lane < 3) {
+        const float v = src[lane];
+        a.x_in[3 * node + lane] = v; a.x_a[3 * node + lane] = v; a.x_b[3 * node + lane] = v;
     }
+    float feat[4] = {lane < nf ? src[3 + lane] : 0.f, lane + 32 < nf ? src[3 + lane + 32] : 0.f, 0.f, 0.f};
+    float hid[4];
+    warp_linear<4>(feat, nf, w0, b0, 2 * nf, lane, hid);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) hid[m] = silu_f(hid[m]);
+    float jo[2];
+    warp_linear<2>(hid, 2 * nf, w2, b2, a.J, lane, jo);
+    float joint[4] = {jo[0], jo[1], 0.f, 0.f};
+    if (a.D > a.J) {                                      // time feature = last input column (dynamics.py:92-99)
+        const int step = a.step_idx ? *a.step_idx : 0;
+        const float t = a.t_base[(size_t)step * a.row_stride + (size_t)a.sample_of[node] * a.t_stride];
+        if (lane == (a.J & 31)) joint[a.J >> 5] = t;
+    }
+    float o[8];
+    warp_linear<8>(joint, a.D, a.embw, a.embb, H, lane, o);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) a.h[(size_t)node * H + lane + 32 * m] = o[m];
 }
 
 // ------------------------------------------------------------------------------------
@@ -71,16 +82,17 @@ struct CoordFinishArgs {
     int Np; float norm_constant, coords_range, norm_factor; int use_tanh, mean;
 };
 
-// One thread per phar row (the only rows update_coords_mask keeps, dynamics.py:105-107); the
-// row's edges are summed sequentially in CSR order, like the reference's index_add on CPU.
-__global__ void __launch_bounds__(128) coord_finish_kernel(CoordFinishArgs a)
+// Eight lanes per phar row (the only rows update_coords_mask keeps, dynamics.py:105-107): lane l takes the
+// row's edges l, l+8, ... in CSR order, then a fixed-order 3-step shuffle tree combines the lanes —
+// deterministic, no atomics.  All loads of a lane are independent, so a row costs two L2 round trips.
+__global__ void __launch_bounds__(256) coord_finish_kernel(CoordFinishArgs a)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.Np) return;
-    const int s = a.rowptr[r], e = a.rowptr[r + 1];
-    const float xi = a.x_cur[3 * r], yi = a.x_cur[3 * r + 1], zi = a.x_cur[3 * r + 2];
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l = threadIdx.x & 7;
+    const bool live = r < a.Np;
+    const int s = live ? a.rowptr[r] : 0, e = live ? a.rowptr[r + 1] : 0;
+    const float xi = live ? a.x_cur[3 * r] : 0.f, yi = live ? a.x_cur[3 * r + 1] : 0.f, zi = live ? a.x_cur[3 * r + 2] : 0.f;
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (int k = s; k < e; ++k) {
+    for (int k = s + l; k < e; k += 8) {
         const int j = a.col[k];
         const float dx = xi - a.x_cur[3 * j], dy = yi - a.x_cur[3 * j + 1], dz = zi - a.x_cur[3 * j + 2];
         const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -90,10 +102,18 @@ __global__ void __launch_bounds__(128) coord_finish_kernel(CoordFinishArgs a)
         if (a.use_tanh) { tx = __fmul_rn(tx, a.coords_range); ty = __fmul_rn(ty, a.coords_range); tz = __fmul_rn(tz, a.coords_range); }
         sx = __fadd_rn(sx, tx); sy = __fadd_rn(sy, ty); sz = __fadd_rn(sz, tz);
     }
-    const float d = a.mean ? (float)max(e - s, 1) : a.norm_factor;
-    a.x_next[3 * r] = __fadd_rn(xi, __fdiv_rn(sx, d));
-    a.x_next[3 * r + 1] = __fadd_rn(yi, __fdiv_rn(sy, d));
-    a.x_next[3 * r + 2] = __fadd_rn(zi, __fdiv_rn(sz, d));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, o, 8));
+        sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, sy, o, 8));
+        sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, sz, o, 8));
+    }
+    if (live && l == 0) {
+        const float d = a.mean ? (float)max(e - s, 1) : a.norm_factor;
+        a.x_next[3 * r] = __fadd_rn(xi, __fdiv_rn(sx, d));
+        a.x_next[3 * r + 1] = __fadd_rn(yi, __fdiv_rn(sy, d));
+        a.x_next[3 * r + 2] = __fadd_rn(zi, __fdiv_rn(sz, d));
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -162,13 +182,13 @@ __global__ void nan_fixup_kernel(float* out_phar, float* out_res, int Np, int Nr
     if (i == 0 && bad) nan_flag[1] += 1;
 }
 
-__global__ void clear_flag_kernel(int* nan_flag) { nan_flag[0] = 0; }
 
 // ------------------------------------------------------------------------------------
 struct DdpmKArgs {
     DdpmArgs d;
     const int* phar_off; const int* res_off;
     int P, R; int* nan_flag; float* stats;
+    int* ticket;                                      // advance: the block that finishes last bumps *step_idx
 };
 
 __device__ __forceinline__ void atomic_max_pos(float* addr, float v)
@@ -237,9 +257,14 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
         float* px = d.pocket + (size_t)(r0 + i) * RW + c;
         *px = __fsub_rn(*px, mean[c]);
     }
+    if (d.advance && tid == 0) {
+        // every block read *step_idx before arriving here; the last one to arrive moves the sampler on
+        // (a control ticket, not a data-path reduction)
+        __threadfence();
+        if (atomicAdd(k.ticket, 1) == (int)gridDim.x - 1) { *k.ticket = 0; *const_cast<int*>(d.step_idx) = *d.step_idx + 1; }
+    }
 }
 
-__global__ void advance_step_kernel(int* step_idx) { step_idx[0] += 1; }
 
 // mu of the initial draw: pocket COM per sample, zero features (conditional_model.py:412-414)
 __global__ void __launch_bounds__(128) pocket_com_init_kernel(float* z, const float* pocket, const int* phar_off,
@@ -278,13 +303,12 @@ int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res,
     a.re0w = w.res_enc0.wt; a.re0b = w.res_enc0.b; a.re2w = w.res_enc2.wt; a.re2b = w.res_enc2.b;
     a.embw = w.emb.wt; a.embb = w.emb.b;
     a.h = p.h; a.x_in = p.x_in; a.x_a = p.x_a; a.x_b = p.x_b;
-    int grid = p.N < h->sm_count * 8 ? p.N : h->sm_count * 8;
-    if (grid < 1) grid = 1;
+    const int grid = (p.N + 7) / 8;
+    a.nan_flag = p.nan_flag;
     prof_begin(h, PROF_OTHER, st);
-    clear_flag_kernel<<<1, 1, 0, st>>>(p.nan_flag);
     encode_nodes_kernel<<<grid, 256, 0, st>>>(a);
     prof_end(h, st);
-    h->launches += 2;
+    h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
 }
@@ -297,7 +321,7 @@ int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStr
     a.x_cur = x_cur; a.x_next = x_next; a.escal = p.escal; a.rowptr = p.rowptr; a.col = p.col;
     a.Np = p.Np; a.norm_constant = c.norm_constant; a.coords_range = c.coords_range;
     a.norm_factor = c.normalization_factor; a.use_tanh = c.use_tanh; a.mean = c.aggregation_mean;
-    coord_finish_kernel<<<(p.Np + 127) / 128, 128, 0, st>>>(a);
+    coord_finish_kernel<<<(p.Np * 8 + 255) / 256, 256, 0, st>>>(a);
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
@@ -340,13 +364,12 @@ int launch_ddpm(dp_handle* h, const DdpmArgs& d, cudaStream_t st)
     const Plan& p = h->plan; const dp_config& c = h->cfg;
     DdpmKArgs k;
     k.d = d; k.phar_off = p.phar_off; k.res_off = p.res_off; k.P = c.phar_nf; k.R = c.residue_nf;
-    k.nan_flag = p.nan_flag; k.stats = p.stats;
+    k.nan_flag = p.nan_flag; k.stats = p.stats; k.ticket = p.counts + 3;
     const size_t smem = ((size_t)p.max_phar * (3 + c.phar_nf) + 4) * sizeof(float);
     DP_CHECK(smem <= 48 * 1024, DP_ERR_INVALID, "ddpm: %d phar nodes in one sample exceed the shared-memory tile", p.max_phar);
     prof_begin(h, PROF_DDPM, st);
     ddpm_kernel<<<p.B, 128, smem, st>>>(k);
     h->launches += 1;
-    if (d.advance) { advance_step_kernel<<<1, 1, 0, st>>>(p.step_idx); h->launches += 1; }
     prof_end(h, st);
     DP_CUDA(cudaGetLastError());
     return DP_OK;

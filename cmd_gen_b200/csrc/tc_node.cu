@@ -1,0 +1,367 @@
+// K2b — the fused per-node phase of one GCL on the 5th-generation tensor cores (DP_BF16 / DP_F16):
+//
+//   t      = SiLU(W3 [h | agg] + b3)                 GCL.node_model, first layer   (egnn_new.py:21-24, 54-56)
+//   h     <- h + W4 t + b4                            second layer + residual        (egnn_new.py:57)
+//   P      = Wp h + bp                                the factored FIRST layers of the consumers of the new h:
+//                                                     (Pa | Pb) of the next GCL's edge MLP and / or (Qa | Qb) of
+//                                                     this block's coordinate MLP — W1 [h_i; h_j; e] = W1a h_i +
+//                                                     W1b h_j + W1c e, so the H x H products are per node
+//
+// One CTA per 128-node tile runs the three GEMMs back to back without leaving the SM: the activations
+// of each stage are written by the epilogue straight into the next stage's swizzled K-major B tile in
+// shared memory (never to HBM), accumulators live in TMEM (2 x 256 columns), and the weight panels
+// (32 KB each: 256 out channels x 64 K, pre-swizzled bf16/f16) stream through a 3-slot ring filled by
+// cp.async.bulk from one concatenated image per launch.  Channels-on-lanes orientation as in
+// tc_edge.cu: D[out channel, node] = W . X^T, so bias / residual / stores are per-lane scalars and
+// 128-byte coalesced rows.
+//
+//   warps 0-15  compute : stage [h | agg] -> bf16 tiles; the three epilogues
+//   warp  16    TMA     : one thread streams the weight panels through the ring
+//   warp  17    MMA     : one thread issues tcgen05.mma (M=128, N=128, K=16), commits to mbarriers
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+constexpr int NT = 128;                          // nodes per tile (UMMA N)
+constexpr int NX_PANEL = NT * 128;               // 16 KB: 128 nodes x 64 K x 2 B
+constexpr int X_BYTES = 4 * NX_PANEL;            // 64 KB: K = 256
+constexpr int N_WS = 3;                          // weight ring slots
+constexpr int COMPUTE_WARPS = 16;
+constexpr int TMA_WARP = 16, MMA_WARP = 17;
+constexpr int THREADS = 18 * 32;
+constexpr int ACC_COLS = 2 * NT;                 // TMEM columns per accumulator (two 128-channel halves)
+
+struct NodeSmem {
+    unsigned char xa[X_BYTES];                   // h tile, later t = SiLU(n0) tile
+    unsigned char xb[X_BYTES];                   // agg tile, later the new-h tile
+    unsigned char w[N_WS][W_PANEL_BYTES];        // 96 KB ring
+    unsigned long long bar_wfull[N_WS], bar_wempty[N_WS];
+    unsigned long long bar_x[3];                 // B tile ready: [h|agg], t, new h
+    unsigned long long bar_accfull[2], bar_accempty[2];
+    uint32_t tmem_holder;
+};
+
+struct NodeArgs {
+    float* h;                                    // [N][H] in / out (in place)
+    AggView aggv;
+    int n_rows;
+    int do_mlp;                                  // 0: projection only (h version 0, straight from the embedding)
+    const float* b3; const float* b4;            // node_mlp biases
+    const float* bp;                             // projection bias [n_blocks * 256]
+    float* pq; int ldp; int n_blocks;            // projection output [N][ldp], n_blocks x 256 channels
+    long long* trace;                            // debug timeline (dp_debug_trace), normally null
+};
+
+// debug timeline of CTA 0: role 0 = compute warp 0, 1 = MMA thread, 2 = TMA thread; 16 slots per (role, row)
+__device__ __forceinline__ void trace_mark(long long* trace, int role, int row, int slot)
+{
+    if (trace && blockIdx.x == 0) trace[(role * 64 + row) * 16 + slot] = clock64();
+}
+
+// 8 MMAs of one K panel: D[256 x 128] (+)= Wpanel[256 x 64] * Xpanel[128 x 64]^T
+__device__ __forceinline__ void issue_panel(uint32_t tmem_d, uint32_t w_slot, uint32_t x_panel, uint32_t idesc, bool first)
+{
+#pragma unroll
+    for (int ks = 0; ks < PANEL_K / 16; ++ks) {
+        const uint64_t bdesc = make_desc(x_panel + ks * 32);
+        const uint32_t acc = (!first || ks > 0) ? 1u : 0u;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t adesc = make_desc(w_slot + hh * (128 * 128) + ks * 32);
+            umma_f16(tmem_d + hh * NT, adesc, bdesc, idesc, acc);
+        }
+    }
+}
+
+__device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
+
+template <int FMT>
+__device__ __forceinline__ uint4 pack8(const float4& f0, const float4& f1)
+{
+    return make_uint4(pack2<FMT>(f0.x, f0.y), pack2<FMT>(f0.z, f0.w), pack2<FMT>(f1.x, f1.y), pack2<FMT>(f1.z, f1.w));
+}
+
+// h rows (fp32) -> swizzled 16-bit K-major tile.  Warp w owns rows 8w .. 8w+7 of the tile; lane = 16-byte
+// chunk; all 16 loads of a warp are in flight together.
+template <int FMT>
+__device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane)
+{
+    float4 f[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int row = n0 + 8 * wid + u;
+        f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.n_rows) {
+            const float* src = a.h + (size_t)row * H + 8 * lane;
+            f[u][0] = *reinterpret_cast<const float4*>(src); f[u][1] = *reinterpret_cast<const float4*>(src + 4);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<uint4*>(tile + chunk_offset(8 * wid + u, lane, NX_PANEL)) = pack8<FMT>(f[u][0], f[u][1]);
+}
+
+// Aggregated messages -> tile.  A row whose edges lie inside one 32-edge unit was stored whole (agg[row]);
+// a row that crosses unit boundaries was stored as per-unit partial sums (see AggView / graph.cu edge_dst):
+// the first two sources of 4 rows are fetched together, longer rows (degree > 32) take a loop.
+// unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a reciprocal multiply.
+template <int FMT>
+__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane)
+{
+    const AggView& g = a.aggv;
+    const int r0 = n0 + 8 * wid;
+    int rp = 0;
+    if (lane < 9) rp = g.rowptr[min(r0 + lane, a.n_rows)];
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        float4 f[4][2], f2[4][2];
+        int s_[4], e_[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = r0 + 4 * hb + u;
+            s_[u] = __shfl_sync(0xffffffffu, rp, 4 * hb + u);
+            e_[u] = __shfl_sync(0xffffffffu, rp, 4 * hb + u + 1);
+            if (row >= a.n_rows) e_[u] = s_[u];
+            f[u][0] = f[u][1] = f2[u][0] = f2[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e_[u] > s_[u]) {
+                const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
+                const float* src = (uf == ul) ? g.agg + (size_t)row * H
+                                              : g.partials + ((size_t)uf * 2 + (s_[u] <= uf * g.unit ? 0 : 1)) * H;
+                f[u][0] = *reinterpret_cast<const float4*>(src + 8 * lane);
+                f[u][1] = *reinterpret_cast<const float4*>(src + 8 * lane + 4);
+                if (ul > uf) {
+                    const float* src2 = g.partials + ((size_t)(uf + 1) * 2) * H;
+                    f2[u][0] = *reinterpret_cast<const float4*>(src2 + 8 * lane);
+                    f2[u][1] = *reinterpret_cast<const float4*>(src2 + 8 * lane + 4);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[8] = {f[u][0].x + f2[u][0].x, f[u][0].y + f2[u][0].y, f[u][0].z + f2[u][0].z, f[u][0].w + f2[u][0].w,
+                          f[u][1].x + f2[u][1].x, f[u][1].y + f2[u][1].y, f[u][1].z + f2[u][1].z, f[u][1].w + f2[u][1].w};
+            if (e_[u] > s_[u]) {
+                const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
+                for (int un = uf + 2; un <= ul; ++un) {                               // degree > 32: rare
+                    const float* src = g.partials + ((size_t)un * 2) * H + 8 * lane;
+                    const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
+                    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                }
+            }
+            const float sc = g.mean ? __fdividef(1.0f, (float)max(e_[u] - s_[u], 1)) : g.inv_norm;
+            *reinterpret_cast<uint4*>(tile + chunk_offset(8 * wid + 4 * hb + u, lane, NX_PANEL)) =
+                make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
+                           pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
+        }
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_k16(unsigned char* tile, int i, int k, float v)
+{
+    unsigned char* p = tile + chunk_offset(i, k >> 3, NX_PANEL) + ((k & 7) << 1);
+    if (FMT == FMT_BF16) *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+    else *reinterpret_cast<__half*>(p) = __float2half_rn(v);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const unsigned char* __restrict__ w_img)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    NodeSmem& s = *reinterpret_cast<NodeSmem*>(base);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n0 = blockIdx.x * NT;
+    const int n_panels = (a.do_mlp ? 12 : 0) + 4 * a.n_blocks;
+
+    if (tid == 0) {
+        for (int i = 0; i < N_WS; ++i) { mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), 1); }
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s.bar_x[i]), COMPUTE_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), COMPUTE_WARPS); }
+        fence_barrier_init();
+    }
+    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), 2 * ACC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_holder;
+
+    if (wid == TMA_WARP) {
+        // ================================ weight stream ================================
+        if (lane == 0) {
+            for (int p = 0; p < n_panels; ++p) {
+                const int slot = p % N_WS;
+                trace_mark(a.trace, 2, p, 0);
+                mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS) & 1) ^ 1);
+                trace_mark(a.trace, 2, p, 1);
+                mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_PANEL_BYTES);
+                bulk_g2s(smem_u32(s.w[slot]), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
+            }
+        }
+    } else if (wid == MMA_WARP) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT, 128, NT);
+            int p = 0;
+            int acc_uses[2] = {0, 0};
+            auto run_gemm = [&](int acc, uint32_t x0, uint32_t x1, int k_panels) {
+                // x0: first 4 panels' tile, x1: panels 4-7 (K = 512 only)
+                if (acc_uses[acc] > 0) mbar_wait(smem_u32(&s.bar_accempty[acc]), (acc_uses[acc] - 1) & 1);
+                tc_fence_after();
+                for (int kp = 0; kp < k_panels; ++kp, ++p) {
+                    const int slot = p % N_WS;
+                    trace_mark(a.trace, 1, p, 0);
+                    mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS) & 1);
+                    trace_mark(a.trace, 1, p, 1);
+                    tc_fence_after();
+                    const uint32_t xp = (kp < 4 ? x0 + kp * NX_PANEL : x1 + (kp - 4) * NX_PANEL);
+                    issue_panel(tmem_base + acc * ACC_COLS, smem_u32(s.w[slot]), xp, idesc, kp == 0);
+                    umma_commit(smem_u32(&s.bar_wempty[slot]));
+                    trace_mark(a.trace, 1, p, 2);
+                }
+                umma_commit(smem_u32(&s.bar_accfull[acc]));
+                acc_uses[acc] += 1;
+            };
+            if (a.do_mlp) {
+                mbar_wait(smem_u32(&s.bar_x[0]), 0);
+                run_gemm(0, smem_u32(s.xa), smem_u32(s.xb), 8);
+                mbar_wait(smem_u32(&s.bar_x[1]), 0);
+                run_gemm(1, smem_u32(s.xa), 0, 4);
+            }
+            mbar_wait(smem_u32(&s.bar_x[2]), 0);
+            for (int b = 0; b < a.n_blocks; ++b) run_gemm(b & 1, smem_u32(s.xb), 0, 4);
+        }
+    } else {
+        // ================================ compute warps ================================
+        const int q = wid & 3, g = wid >> 2, half = g & 1, nh = g >> 1;
+        const int ch = 128 * half + 32 * q + lane;
+        const uint32_t t_lane = (uint32_t)(32 * q) << 16;
+        int acc_uses[2] = {0, 0};
+        auto wait_acc = [&](int acc) {
+            mbar_wait(smem_u32(&s.bar_accfull[acc]), acc_uses[acc] & 1);
+            acc_uses[acc] += 1;
+            tc_fence_after();
+        };
+        auto release_acc = [&](int acc) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.bar_accempty[acc]));
+        };
+        auto publish = [&](int which) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.bar_x[which]));
+        };
+        const bool tr = wid == 0 && lane == 0;
+        if (tr) trace_mark(a.trace, 0, 0, 0);
+        if (a.do_mlp) {
+            stage_h<FMT>(s.xa, a, n0, wid, lane);
+            if (tr) trace_mark(a.trace, 0, 0, 1);
+            stage_agg<FMT>(s.xb, a, n0, wid, lane);
+            publish(0);
+            if (tr) trace_mark(a.trace, 0, 0, 2);
+            // ---- epilogue 1: t = SiLU(D1 + b3) -> xa (the n0 MMAs have all retired: acc_full follows them)
+            const float b3c = a.b3[ch];
+            wait_acc(0);
+            if (tr) trace_mark(a.trace, 0, 0, 3);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[32];
+                tmem_ld32(tmem_base + t_lane + half * NT + 64 * nh + 32 * pass, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) store_k16<FMT>(s.xa, 64 * nh + 32 * pass + j, ch, silu_tc<FMT>(v[j] + b3c));
+            }
+            release_acc(0);
+            publish(1);
+            if (tr) trace_mark(a.trace, 0, 0, 4);
+            // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> xb
+            const float b4c = a.b4[ch];
+            float r[32];                                                             // residual rows of pass 0: fetched under the MMAs
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = (n0 + 64 * nh + j < a.n_rows) ? a.h[(size_t)(n0 + 64 * nh + j) * H + ch] : 0.f;
+            wait_acc(1);
+            if (tr) trace_mark(a.trace, 0, 0, 5);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[32];
+                const int i0 = 64 * nh + 32 * pass;
+                if (pass == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = (n0 + i0 + j < a.n_rows) ? a.h[(size_t)(n0 + i0 + j) * H + ch] : 0.f;
+                }
+                tmem_ld32(tmem_base + ACC_COLS + t_lane + half * NT + i0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float o = r[j] + (v[j] + b4c);
+                    if (n0 + i0 + j < a.n_rows) a.h[(size_t)(n0 + i0 + j) * H + ch] = o;
+                    store_k16<FMT>(s.xb, i0 + j, ch, (n0 + i0 + j < a.n_rows) ? o : 0.f);
+                }
+            }
+            release_acc(1);
+            publish(2);
+            if (tr) trace_mark(a.trace, 0, 0, 6);
+        } else {
+            stage_h<FMT>(s.xb, a, n0, wid, lane);
+            publish(2);
+        }
+        // ---- epilogue 3: projection blocks -> P (fp32)
+        for (int b = 0; b < a.n_blocks; ++b) {
+            const int acc = b & 1;
+            const float bias = a.bp[b * 256 + ch];
+            float* dst = a.pq + (size_t)b * 256 + ch;
+            wait_acc(acc);
+            if (tr) trace_mark(a.trace, 0, 0, 7 + 2 * b);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                float v[32];
+                const int i0 = 64 * nh + 32 * pass;
+                tmem_ld32(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
+                if (pass == 1) release_acc(acc);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + i0 + j < a.n_rows) dst[(size_t)(n0 + i0 + j) * a.ldp] = v[j] + bias;
+            }
+            if (tr) trace_mark(a.trace, 0, 0, 8 + 2 * b);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == MMA_WARP) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+}  // namespace
+
+int tc_node_init()
+{
+    static_assert(sizeof(NodeSmem) + 1024 <= 232448, "node kernel shared memory exceeds 227 KB");
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    return DP_OK;
+}
+
+// One launch per h version v: v = 0 is the projection of the embedded features; v = i + 1 runs GCL i's node
+// model and then projects the new h for its consumers.
+int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
+{
+    int fmt = 0, rc = tc_fmt_of(h, &fmt);
+    if (rc) return rc;
+    Plan& p = h->plan; const DeviceWeights& W = h->w;
+    DP_CHECK(h->tc && v >= 0 && v < (int)h->tc->node.size() && h->tc->node[v].img[fmt], DP_ERR_STATE,
+             "tc node phase %d has no weight image", v);
+    const ProjSet& ps = W.proj[v];
+    NodeArgs a{};
+    a.h = p.h; a.aggv = av; a.n_rows = p.N; a.do_mlp = v > 0;
+    if (v > 0) { a.b3 = W.gcl[v - 1].n0.b; a.b4 = W.gcl[v - 1].n2.b; }
+    a.bp = ps.lin.b; a.pq = p.pq; a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
+    a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
+    DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
+    if (p.N <= 0) return DP_OK;
+    const int grid = (p.N + NT - 1) / NT;
+    const int smem = (int)sizeof(NodeSmem) + 1024;
+    if (fmt == tc::FMT_BF16) node_tc_kernel<tc::FMT_BF16><<<grid, THREADS, smem, st>>>(a, h->tc->node[v].img[fmt]);
+    else node_tc_kernel<tc::FMT_F16><<<grid, THREADS, smem, st>>>(a, h->tc->node[v].img[fmt]);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}

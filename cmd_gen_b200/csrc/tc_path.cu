@@ -188,6 +188,7 @@ uint16_t f32_to_f16(float f)
 int tc_init()
 {
     int rc = tc_edge_init();
+    if (!rc) rc = tc_node_init();
     if (rc) return rc;
     DP_CUDA(cudaFuncSetAttribute(linear_tc_kernel<FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinTcSmem) + 1024));
     DP_CUDA(cudaFuncSetAttribute(linear_tc_kernel<FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinTcSmem) + 1024));
@@ -235,6 +236,33 @@ int tc_prepare_weights(dp_handle* h)
             T.lin[id].img[fmt] = reinterpret_cast<unsigned char*>(d);
         }
         T.lin[id].K = L.K; T.lin[id].n_out = L.n_out;
+    }
+    // Fused node-phase launches (tc_node.cu) stream ONE contiguous panel sequence: for h version v > 0 the
+    // node MLP of GCL v-1 (node_mlp.0: 8 panels, node_mlp.2: 4 panels) followed by the projection blocks of
+    // the new h; v = 0 is the projection of the embedded features alone.
+    const dp_config& c = h->cfg;
+    const int G = c.n_layers * c.inv_sublayers;
+    T.node.resize(G + 1);
+    for (int v = 0; v <= G; ++v) {
+        std::vector<int> parts;
+        if (v > 0) { parts.push_back(4 * (v - 1) + 1); parts.push_back(4 * (v - 1) + 2); }
+        parts.push_back(4 * G + c.n_layers + v);
+        size_t bytes = 0;
+        for (int id : parts) bytes += (size_t)(T.lin[id].K / PANEL_K) * (T.lin[id].n_out / 256) * W_PANEL_BYTES;
+        T.node[v].n_panels = (int)(bytes / W_PANEL_BYTES);
+        if (bytes == 0) continue;
+        for (int fmt = 0; fmt < 2; ++fmt) {
+            void* d = nullptr;
+            DP_CUDA(cudaMalloc(&d, bytes));
+            T.allocations.push_back(d);
+            size_t off = 0;
+            for (int id : parts) {
+                const size_t b = (size_t)(T.lin[id].K / PANEL_K) * (T.lin[id].n_out / 256) * W_PANEL_BYTES;
+                if (b) DP_CUDA(cudaMemcpy(reinterpret_cast<unsigned char*>(d) + off, T.lin[id].img[fmt], b, cudaMemcpyDeviceToDevice));
+                off += b;
+            }
+            T.node[v].img[fmt] = reinterpret_cast<unsigned char*>(d);
+        }
     }
     return DP_OK;
 }

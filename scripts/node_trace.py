@@ -1,10 +1,10 @@
-"""GPU debug tool: per-role clock64 timeline of CTA 0 of the tcgen05 edge kernel (last message-kernel launch
-of one denoiser evaluation at config-2 size).  DIFFPHAR_TRACE=1 python scripts/edge_trace.py [precision]"""
+"""GPU debug tool: clock64 timeline of CTA 0 of the fused tcgen05 node kernel (last launch of one denoiser
+evaluation at config-2 size).  python scripts/node_trace.py [precision]"""
 import ctypes as C
 import os
 import sys
 
-os.environ["DIFFPHAR_TRACE"] = "2"
+os.environ["DIFFPHAR_TRACE"] = "1"
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cmd_gen_b200 import _lib
@@ -30,20 +30,14 @@ torch.cuda.synchronize()
 n = 3 * 64 * 16
 buf = (C.c_longlong * n)()
 h.lib.dp_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
-rc = h.lib.dp_debug_trace(h.h, buf, n)
-assert rc == 0, h.lib.dp_last_error()
+assert h.lib.dp_debug_trace(h.h, buf, n) == 0, h.lib.dp_last_error()
 tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(3)]
 t0 = min(v for r in tr for it in r for v in it if v > 0)
-names = {0: ["start", "xempty", "b0 issued", "b0 done", "b1 issued", "b1 done", "arrive"],
-         1: ["start", "full", "tempty", "issued"],
-         2: ["start", "tfull", "ld0", "silu0", "red0", "bar0", "gate0", "bcast0", "seg0",
-             "ld1", "silu1", "red1", "bar1", "gate1", "bcast1", "seg1"]}
-print("E =", h.flags().last_n_edges, " (cycles relative to the first mark, CTA 0)")
-w = tr[1][63]
-print(f"weights: issue {w[0] - t0}  landed {w[1] - t0}")
-for it in range(10):
-    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue")):
-        row = tr[r][it]
-        if not any(row):
-            continue
-        print(f"it {it} {rn:9s} " + "  ".join(f"{nm}={row[k] - t0}" for k, nm in enumerate(names[r]) if row[k]))
+cn = ["start", "h staged", "agg staged", "acc0 full", "t stored", "acc1 full", "h stored"] + \
+     [f"{w}{b}" for b in range(4) for w in ("P full ", "P stored ")]
+print("compute warp 0: " + "  ".join(f"{nm}={tr[0][0][k] - t0}" for k, nm in enumerate(cn) if k < 16 and tr[0][0][k]))
+for p in range(32):
+    m, w = tr[1][p], tr[2][p]
+    if not any(m) and not any(w):
+        continue
+    print(f"panel {p:2d}  tma: wait {w[0] - t0} issue {w[1] - t0}   mma: wait {m[0] - t0} full {m[1] - t0} issued {m[2] - t0}")
