@@ -357,7 +357,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1);
     ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.edst, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
     ALLOC(p.counts, 4);
-    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H);
+    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.h_base, (size_t)p.Nr * H);
     ALLOC(p.agg, ((size_t)p.N + units * 2) * H);          // [agg rows | partial rows] contiguous (graph.cu edge_dst)
     p.partials = p.agg + (size_t)p.N * H;
     ALLOC(p.pq, (size_t)p.N * 4 * H);
@@ -458,13 +458,13 @@ static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st
 // 4i+2 = node_mlp.2; per block b: 4G + b = coord_mlp.2; projections: 4G + L + v.
 static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
                         const int* step_idx, int row_stride, int t_stride, float* out_phar, float* out_res,
-                        cudaStream_t st)
+                        cudaStream_t st, bool pocket_base = false)
 {
     Plan& p = h->plan; const dp_config& c = h->cfg; DeviceWeights& W = h->w;
     const int S = c.inv_sublayers, G = c.n_layers * S;
     const int unit = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? UNIT_F32 : UNIT_TC;
     int rc = 0;
-    if ((rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, st))) return rc;
+    if ((rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
     if ((rc = launch_build_edges(h, p.x_in, st))) return rc;
     float* x_cur = p.x_a; float* x_next = p.x_b;
 
@@ -571,7 +571,7 @@ static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise
 {
     Plan& p = h->plan; const dp_config& c = h->cfg;
     const int PW = 3 + c.phar_nf;
-    int rc = run_denoiser(h, p.z, pocket, p.step_rows, p.step_idx, 4, 0, p.eps_hat, nullptr, st);
+    int rc = run_denoiser(h, p.z, pocket, p.step_rows, p.step_idx, 4, 0, p.eps_hat, nullptr, st, true);
     if (rc) return rc;
     DdpmArgs d{};
     d.kind = 0; d.table = p.step_rows; d.step_idx = p.step_idx;
@@ -594,6 +594,8 @@ extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float*
     DP_CUDA(cudaMemsetAsync(p.step_idx, 0, sizeof(int), st));
     DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
     DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, sizeof(int), st));
+    // the pocket's type features never change while sampling: embed them once, without the time term
+    if ((rc = launch_encode_nodes(h, p.z, pocket, p.t_const, nullptr, 0, 0, 1, st))) return rc;
     // z_T ~ N(pocket COM, I), projected (conditional_model.py:412-418)
     if ((rc = launch_pocket_com_init(h, p.z, pocket, st))) return rc;
     DdpmArgs d0{};
@@ -629,7 +631,7 @@ extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float*
     }
     // p(x | z0): conditional_model.py:108-131
     DP_CUDA(cudaMemcpyAsync(p.t_const, &h->final_host[0], sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = run_denoiser(h, p.z, pocket, p.t_const, nullptr, 0, 0, p.eps_hat, nullptr, st))) return rc;
+    if ((rc = run_denoiser(h, p.z, pocket, p.t_const, nullptr, 0, 0, p.eps_hat, nullptr, st, true))) return rc;
     DP_CUDA(cudaMemcpyAsync(out_phar, p.z, zbytes, cudaMemcpyDeviceToDevice, st));          // keeps z0's feature columns
     DdpmArgs df{};
     df.kind = 1; df.a = h->final_host[1]; df.c = h->final_host[2]; df.sigma = h->final_host[3];

@@ -142,6 +142,7 @@ struct Plan {
     int* counts = nullptr;       // [4]: E, E_p, overflow, spare
     // node state
     float* h = nullptr;          // [N][H]
+    float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
     float* tbuf = nullptr;       // [N][H] node-MLP hidden
     float* agg = nullptr;        // [N][H]
     float* partials = nullptr;   // [units][2][H]
@@ -238,8 +239,10 @@ int launch_edge_f32(dp_handle* h, const EdgeArgs& a, cudaStream_t st);
 int egnn_f32_init();
 
 // small.cu
+// base_mode 0: full encoders for every node; 1: write plan.h_base for the pocket nodes only (no time term);
+// 2: pocket nodes = h_base + t * w_time (their type features are constant during sampling), phar nodes in full
 int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
-                        const int* step_idx, int row_stride, int t_stride, cudaStream_t st);
+                        const int* step_idx, int row_stride, int t_stride, int base_mode, cudaStream_t st);
 int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStream_t st);
 int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* out_res, cudaStream_t st);
 int launch_nan_fixup(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st);

@@ -20,6 +20,7 @@ struct EncodeArgs {
     const float *embw, *embb;                         // [D][H], [H]
     float* h; float* x_in; float* x_a; float* x_b;
     int* nan_flag;                                    // [0] cleared here: first kernel of every denoiser evaluation
+    float* h_base; int base_mode;                     // see launch_encode_nodes
 };
 
 // One warp per node.  Every layer is out[o] = b[o] + sum_k in[k] w[k][o] with the outputs spread over
@@ -45,9 +46,31 @@ __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0) a.nan_flag[0] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.base_mode != 1) a.nan_flag[0] = 0;
     if (node >= a.N) return;
     const bool phar = node < a.Np;
+    if (a.base_mode == 1 && phar) return;
+    if (a.base_mode == 2 && !phar) {
+        // pocket node during sampling: features are constant, only the time column moves.  The time weight is the
+        // LAST term of the reference's accumulation chain, so base + t * w_time is bit-identical to the full path.
+        const float* src = a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
+        if (lane < 3) {
+            const float v = src[lane];
+            a.x_in[3 * node + lane] = v; a.x_a[3 * node + lane] = v; a.x_b[3 * node + lane] = v;
+        }
+        float t = 0.f;
+        if (a.D > a.J) {
+            const int step = a.step_idx ? *a.step_idx : 0;
+            t = a.t_base[(size_t)step * a.row_stride + (size_t)a.sample_of[node] * a.t_stride];
+        }
+        const float* base = a.h_base + (size_t)(node - a.Np) * H;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int c = lane + 32 * m;
+            a.h[(size_t)node * H + c] = (a.D > a.J) ? fmaf(t, a.embw[(size_t)a.J * H + c], base[c]) : base[c];
+        }
+        return;
+    }
     const int nf = phar ? a.P : a.R;
     const float* src = phar ? a.xh_phar + (size_t)node * (3 + a.P) : a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
     const float *w0 = phar ? a.pe0w : a.re0w, *b0 = phar ? a.pe0b : a.re0b;
@@ -70,6 +93,12 @@ __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
         if (lane == (a.J & 31)) joint[a.J >> 5] = t;
     }
     float o[8];
+    if (a.base_mode == 1) {                               // everything but the time term, for mode 2 to finish
+        warp_linear<8>(joint, a.J, a.embw, a.embb, H, lane, o);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a.h_base[(size_t)(node - a.Np) * H + lane + 32 * m] = o[m];
+        return;
+    }
     warp_linear<8>(joint, a.D, a.embw, a.embb, H, lane, o);
 #pragma unroll
     for (int m = 0; m < 8; ++m) a.h[(size_t)node * H + lane + 32 * m] = o[m];
@@ -291,7 +320,7 @@ __global__ void __launch_bounds__(128) pocket_com_init_kernel(float* z, const fl
 
 // ======================================================================================
 int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
-                        const int* step_idx, int row_stride, int t_stride, cudaStream_t st)
+                        const int* step_idx, int row_stride, int t_stride, int base_mode, cudaStream_t st)
 {
     const Plan& p = h->plan; const DeviceWeights& w = h->w; const dp_config& c = h->cfg;
     EncodeArgs a;
@@ -304,7 +333,7 @@ int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res,
     a.embw = w.emb.wt; a.embb = w.emb.b;
     a.h = p.h; a.x_in = p.x_in; a.x_a = p.x_a; a.x_b = p.x_b;
     const int grid = (p.N + 7) / 8;
-    a.nan_flag = p.nan_flag;
+    a.nan_flag = p.nan_flag; a.h_base = p.h_base; a.base_mode = base_mode;
     prof_begin(h, PROF_OTHER, st);
     encode_nodes_kernel<<<grid, 256, 0, st>>>(a);
     prof_end(h, st);

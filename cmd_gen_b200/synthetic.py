@@ -52,3 +52,33 @@ def draw_noise(n_draws: int, n_phar_nodes: int, width: int, seed: int = 123) -> 
     gen = torch.Generator(device="cpu")
     gen.manual_seed(seed)
     return torch.randn(n_draws, n_phar_nodes, width, generator=gen, dtype=torch.float32)
+
+
+def write_synthetic_pdb(path, n_res: int = 60, seed: int = 7, ligand_resseq: int = 901, chain: str = "A") -> int:
+    """A small fake protein (backbone + CB per residue, C-alpha-like density) with one HETATM ligand at its
+    centre — enough for the generate_phars CLI / pocket-selection path.  Returns the number of residues."""
+    from .constants import THREE_TO_ONE
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    ca = ball_points(n_res, CA_DENSITY, gen) + torch.tensor([12.0, -7.5, 30.25])
+    names = sorted(THREE_TO_ONE)
+    types = torch.randint(0, len(names), (n_res,), generator=gen).tolist()
+    offs = {"N": (-1.2, 0.4, 0.1), "CA": (0.0, 0.0, 0.0), "C": (1.1, 0.7, -0.2), "O": (1.6, 1.7, 0.3), "CB": (0.1, -1.2, 0.9)}
+    elem = {"N": "N", "CA": "C", "C": "C", "O": "O", "CB": "C"}
+    lines, serial = [], 1
+    for i in range(n_res):
+        for an, d in offs.items():
+            x, y, z = (ca[i] + torch.tensor(d)).tolist()
+            lines.append("ATOM  %5d %-4s %3s %1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s" %
+                         (serial, " " + an if len(an) < 4 else an, names[types[i]], chain, i + 1, x, y, z, 1.0, 20.0, elem[an]))
+            serial += 1
+    com = ca.mean(0)
+    for k, d in enumerate([(0.0, 0.0, 0.0), (1.4, 0.2, -0.3), (-0.8, 1.1, 0.6), (0.3, -1.3, 1.0)]):
+        x, y, z = (com + torch.tensor(d)).tolist()
+        lines.append("HETATM%5d %-4s %3s %1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s" %
+                     (serial, " C%d" % (k + 1), "LIG", chain, ligand_resseq, x, y, z, 1.0, 30.0, "C"))
+        serial += 1
+    lines.append("END")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return n_res
