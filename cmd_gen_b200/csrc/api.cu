@@ -107,6 +107,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     h->precision = cfg->precision;
     DP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (const char* m = getenv("DIFFPHAR_TC_MASK")) h->tc_mask = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
             h->trace_kernel = atoi(m);
@@ -441,7 +442,8 @@ extern "C" int dp_get_graph(dp_handle* h, const int32_t** rowptr, const int32_t*
 static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st)
 {
     prof_begin(h, PROF_NODE, st);
-    int rc = (h->precision == DP_FP32 || !(h->tc_mask & 2)) ? launch_linear_f32(h, a, st) : launch_linear_tc(h, a, lin_id, st);
+    (void)lin_id;                                    // the tcgen05 path runs the fused node kernel instead (tc_node.cu)
+    int rc = launch_linear_f32(h, a, st);
     prof_end(h, st);
     return rc;
 }

@@ -31,6 +31,27 @@ void dp_set_error(const char* fmt, ...);
     } while (0)
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may begin while its predecessor
+// in the stream drains; everything before pdl_wait() must touch only launch-invariant data (weights, the
+// plan's layout arrays), everything after sees the predecessor's memory.  Without the attribute both
+// instructions are no-ops.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // device-side math shared by kernels
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
@@ -115,7 +136,7 @@ struct DeviceWeights {
     std::vector<void*> allocations;
 };
 
-struct TcWeights;   // tcgen05 operand images (tc_path.cu)
+struct TcWeights;   // tcgen05 operand images (tc_weights.cu)
 struct HostLinear {  // k-major fp32 host copy of a linear the tensor-core path packs: wt[k * n_out + o]
     std::vector<float> wt;
     int K = 0, n_out = 0;
@@ -177,6 +198,7 @@ struct dp_handle {
     int device = 0;
     int sm_count = 148;
     int precision = 0;
+    bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
     DeviceWeights w;
@@ -259,11 +281,10 @@ struct DdpmArgs {
 int launch_ddpm(dp_handle* h, const DdpmArgs& a, cudaStream_t st);
 int launch_pocket_com_init(dp_handle* h, float* z, const float* pocket, cudaStream_t st);
 
-// tc_path.cu (tcgen05)
+// tc_weights.cu (tcgen05)
 int tc_init();
 int tc_prepare_weights(dp_handle* h);
 void tc_free_weights(dp_handle* h);
-int launch_linear_tc(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);
 int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);   // tc_edge.cu
 int tc_edge_init();
 int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st);                 // tc_node.cu

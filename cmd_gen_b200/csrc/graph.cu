@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.N; row += gridDim.x * warps_per_block) {
         const int b = a.sample_of[row];
         const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     if (tid == 0) carry_s = 0;
     __syncthreads();
     for (int base = 0; base < N; base += 1024) {
@@ -150,9 +154,9 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     prof_begin(h, PROF_GRAPH, st);
-    radius_rows_kernel<false><<<grid, 256, 0, st>>>(a);
-    scan_rowptr_kernel<<<1, 1024, 0, st>>>(p.deg, p.rowptr, p.N, p.Np, p.counts, p.Ecap);
-    radius_rows_kernel<true><<<grid, 256, 0, st>>>(a);
+    DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));
+    DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
+    DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<true>, dim3(grid), dim3(256), 0, st, a));
     prof_end(h, st);
     h->launches += 3;
     DP_CUDA(cudaGetLastError());

@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
 {
     const int lane = threadIdx.x & 31;
     const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.base_mode != 1) a.nan_flag[0] = 0;
     if (node >= a.N) return;
     const bool phar = node < a.Np;
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(256) coord_finish_kernel(CoordFinishArgs a)
 {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l = threadIdx.x & 7;
     const bool live = r < a.Np;
+    pdl_launch_dependents();
+    pdl_wait();
     const int s = live ? a.rowptr[r] : 0, e = live ? a.rowptr[r + 1] : 0;
     const float xi = live ? a.x_cur[3 * r] : 0.f, yi = live ? a.x_cur[3 * r + 1] : 0.f, zi = live ? a.x_cur[3 * r + 2] : 0.f;
     float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a)
     __shared__ float joint[64];
     __shared__ float hid[128];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int node = blockIdx.x; node < a.n_nodes; node += gridDim.x) {
         const bool phar = node < a.Np;
         const int nf = phar ? a.P : a.R;
@@ -230,6 +236,8 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
     extern __shared__ float buf[];             // [n_p][D] new values, then mean[3]
     const DdpmArgs& d = k.d;
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int D = 3 + k.P, RW = 3 + k.R;
     const int p0 = k.phar_off[b], np = k.phar_off[b + 1] - p0;
     const int r0 = k.res_off[b], nr = k.res_off[b + 1] - r0;
@@ -335,7 +343,7 @@ int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res,
     const int grid = (p.N + 7) / 8;
     a.nan_flag = p.nan_flag; a.h_base = p.h_base; a.base_mode = base_mode;
     prof_begin(h, PROF_OTHER, st);
-    encode_nodes_kernel<<<grid, 256, 0, st>>>(a);
+    DP_CUDA(launch_kernel(h->pdl, encode_nodes_kernel, dim3(grid), dim3(256), 0, st, a));
     prof_end(h, st);
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
@@ -350,7 +358,7 @@ int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStr
     a.x_cur = x_cur; a.x_next = x_next; a.escal = p.escal; a.rowptr = p.rowptr; a.col = p.col;
     a.Np = p.Np; a.norm_constant = c.norm_constant; a.coords_range = c.coords_range;
     a.norm_factor = c.normalization_factor; a.use_tanh = c.use_tanh; a.mean = c.aggregation_mean;
-    coord_finish_kernel<<<(p.Np * 8 + 255) / 256, 256, 0, st>>>(a);
+    DP_CUDA(launch_kernel(h->pdl, coord_finish_kernel, dim3((p.Np * 8 + 255) / 256), dim3(256), 0, st, a));
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
@@ -371,7 +379,7 @@ int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* ou
     if (a.n_nodes == 0) return DP_OK;
     int grid = a.n_nodes < h->sm_count * 8 ? a.n_nodes : h->sm_count * 8;
     prof_begin(h, PROF_OTHER, st);
-    decode_kernel<<<grid, 256, 0, st>>>(a);
+    DP_CUDA(launch_kernel(h->pdl, decode_kernel, dim3(grid), dim3(256), 0, st, a));
     prof_end(h, st);
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
@@ -397,7 +405,7 @@ int launch_ddpm(dp_handle* h, const DdpmArgs& d, cudaStream_t st)
     const size_t smem = ((size_t)p.max_phar * (3 + c.phar_nf) + 4) * sizeof(float);
     DP_CHECK(smem <= 48 * 1024, DP_ERR_INVALID, "ddpm: %d phar nodes in one sample exceed the shared-memory tile", p.max_phar);
     prof_begin(h, PROF_DDPM, st);
-    ddpm_kernel<<<p.B, 128, smem, st>>>(k);
+    DP_CUDA(launch_kernel(h->pdl, ddpm_kernel, dim3(p.B), dim3(128), smem, st, k));
     h->launches += 1;
     prof_end(h, st);
     DP_CUDA(cudaGetLastError());

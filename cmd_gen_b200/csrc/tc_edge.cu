@@ -4,7 +4,7 @@
 //   coord mode   : EquivariantUpdate.coord_mlp up to its per-edge scalar  (egnn_new.py:87-91)
 //
 // Per 64-edge tile:   X = SiLU(Pa[row] + Pb[col] + r2 wr + d0 wd)            first layer (factored: the two
-//                                                                            H x H products are per NODE, tc_path.cu)
+//                                                                            H x H products are per NODE, tc_node.cu)
 //                     D[256 ch, 64 edges] = W2[256, 256] . X^T              tcgen05.mma, fp32 accumulators in TMEM
 //                     m = SiLU(D + b2);  g = sigmoid(wa . m + ba);  agg[row] += g m
 //
@@ -91,11 +91,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     EdgeSmem& s = *reinterpret_cast<EdgeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int E = *a.n_edges;
-    const int n_tiles = (E + TILE - 1) / TILE;
-    if ((int)blockIdx.x >= n_tiles) return;           // uniform per CTA, before any barrier / allocation
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
+    // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
     if (tid == 0) {
         mbar_init(smem_u32(&s.bar_w), 1);
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
@@ -107,15 +104,23 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_holder;
+    if (wid == MMA_WARP && lane == 0) {
+        const uint32_t bar_w = smem_u32(&s.bar_w);
+        mbar_expect_tx(bar_w, 4 * W_PANEL_BYTES);
+        for (int p = 0; p < 4; ++p)
+            bulk_g2s(smem_u32(s.w + p * W_PANEL_BYTES), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, bar_w);
+    }
+    pdl_launch_dependents();
+    pdl_wait();                                       // from here on: data written by earlier kernels of the step
+    const int E = *a.n_edges;
+    const int n_tiles = (E + TILE - 1) / TILE;
+    const int my_tiles = max(0, (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);   // 0: idle CTA, falls through
 
     if (wid >= MMA_WARP) {
         // ================================ MMA issuer ================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
         if (wid == MMA_WARP && lane == 0) {
             const uint32_t bar_w = smem_u32(&s.bar_w);
-            mbar_expect_tx(bar_w, 4 * W_PANEL_BYTES);
-            for (int p = 0; p < 4; ++p)
-                bulk_g2s(smem_u32(s.w + p * W_PANEL_BYTES), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, bar_w);
             constexpr uint32_t idesc = make_idesc(FMT, 128, TILE);
             trace_mark(a.trace, 1, 63, 0);
             mbar_wait(bar_w, 0);
@@ -366,8 +371,9 @@ int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
     DP_CHECK(L.K == H && L.n_out == H, DP_ERR_INVALID, "tc edge layer %d: shape mismatch", lin_id);
     const int smem = (int)sizeof(EdgeSmem) + 1024;
     const int grid = h->sm_count;
-    if (fmt == tc::FMT_BF16) edge_tc_kernel<tc::FMT_BF16><<<grid, THREADS, smem, st>>>(a, L.img[fmt]);
-    else edge_tc_kernel<tc::FMT_F16><<<grid, THREADS, smem, st>>>(a, L.img[fmt]);
+    const unsigned char* img = L.img[fmt];
+    if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16>, dim3(grid), dim3(THREADS), smem, st, a, img));
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;

@@ -7,26 +7,28 @@
 //                                                     this block's coordinate MLP — W1 [h_i; h_j; e] = W1a h_i +
 //                                                     W1b h_j + W1c e, so the H x H products are per node
 //
-// One CTA per 128-node tile runs the three GEMMs back to back without leaving the SM: the activations
+// One CTA per 96-node tile runs the three GEMMs back to back without leaving the SM: the activations
 // of each stage are written by the epilogue straight into the next stage's swizzled K-major B tile in
-// shared memory (never to HBM), accumulators live in TMEM (2 x 256 columns), and the weight panels
-// (32 KB each: 256 out channels x 64 K, pre-swizzled bf16/f16) stream through a 3-slot ring filled by
+// shared memory (never to HBM), accumulators live in TMEM (2 x 192 columns), and the weight panels
+// (32 KB each: 256 out channels x 64 K, pre-swizzled bf16/f16) stream through a 4-slot ring filled by
 // cp.async.bulk from one concatenated image per launch.  Channels-on-lanes orientation as in
 // tc_edge.cu: D[out channel, node] = W . X^T, so bias / residual / stores are per-lane scalars and
 // 128-byte coalesced rows.
 //
 //   warps 0-15  compute : stage [h | agg] -> bf16 tiles; the three epilogues
 //   warp  16    TMA     : one thread streams the weight panels through the ring
-//   warp  17    MMA     : one thread issues tcgen05.mma (M=128, N=128, K=16), commits to mbarriers
+//   warp  17    MMA     : one thread issues tcgen05.mma (M=128, N=96, K=16), commits to mbarriers
 #include "tc_common.cuh"
 
 namespace {
 using namespace tc;
 
-constexpr int NT = 128;                          // nodes per tile (UMMA N)
-constexpr int NX_PANEL = NT * 128;               // 16 KB: 128 nodes x 64 K x 2 B
-constexpr int X_BYTES = 4 * NX_PANEL;            // 64 KB: K = 256
-constexpr int N_WS = 3;                          // weight ring slots
+constexpr int NT = 96;                           // nodes per tile (UMMA N): 106 CTAs at N = 10 112, and room for a 4-slot ring
+constexpr int NX_PANEL = NT * 128;               // 12 KB: 96 nodes x 64 K x 2 B
+constexpr int X_BYTES = 4 * NX_PANEL;            // 48 KB: K = 256
+constexpr int N_WS = 4;                          // weight ring slots (the stream is latency-bound: depth = throughput)
+constexpr int ROWS_PER_WARP = NT / 16;           // staging: 6 rows per compute warp
+constexpr int COLS_PER_WARP = NT / 2;            // epilogues: 48 node columns per warp, as 3 chunks of 16
 constexpr int COMPUTE_WARPS = 16;
 constexpr int TMA_WARP = 16, MMA_WARP = 17;
 constexpr int THREADS = 18 * 32;
@@ -35,7 +37,7 @@ constexpr int ACC_COLS = 2 * NT;                 // TMEM columns per accumulator
 struct NodeSmem {
     unsigned char xa[X_BYTES];                   // h tile, later t = SiLU(n0) tile
     unsigned char xb[X_BYTES];                   // agg tile, later the new-h tile
-    unsigned char w[N_WS][W_PANEL_BYTES];        // 96 KB ring
+    unsigned char w[N_WS][W_PANEL_BYTES];        // 128 KB ring
     unsigned long long bar_wfull[N_WS], bar_wempty[N_WS];
     unsigned long long bar_x[3];                 // B tile ready: [h|agg], t, new h
     unsigned long long bar_accfull[2], bar_accempty[2];
@@ -82,15 +84,15 @@ __device__ __forceinline__ uint4 pack8(const float4& f0, const float4& f1)
     return make_uint4(pack2<FMT>(f0.x, f0.y), pack2<FMT>(f0.z, f0.w), pack2<FMT>(f1.x, f1.y), pack2<FMT>(f1.z, f1.w));
 }
 
-// h rows (fp32) -> swizzled 16-bit K-major tile.  Warp w owns rows 8w .. 8w+7 of the tile; lane = 16-byte
-// chunk; all 16 loads of a warp are in flight together.
+// h rows (fp32) -> swizzled 16-bit K-major tile.  Warp w owns rows 6w .. 6w+5 of the tile; lane = 16-byte
+// chunk; all 12 loads of a warp are in flight together.
 template <int FMT>
 __device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane)
 {
-    float4 f[8][2];
+    float4 f[ROWS_PER_WARP][2];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int row = n0 + 8 * wid + u;
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+        const int row = n0 + ROWS_PER_WARP * wid + u;
         f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < a.n_rows) {
             const float* src = a.h + (size_t)row * H + 8 * lane;
@@ -98,30 +100,29 @@ __device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, 
         }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<uint4*>(tile + chunk_offset(8 * wid + u, lane, NX_PANEL)) = pack8<FMT>(f[u][0], f[u][1]);
+    for (int u = 0; u < ROWS_PER_WARP; ++u)
+        *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + u, lane, NX_PANEL)) = pack8<FMT>(f[u][0], f[u][1]);
 }
 
 // Aggregated messages -> tile.  A row whose edges lie inside one 32-edge unit was stored whole (agg[row]);
 // a row that crosses unit boundaries was stored as per-unit partial sums (see AggView / graph.cu edge_dst):
-// the first two sources of 4 rows are fetched together, longer rows (degree > 32) take a loop.
+// the first two sources of 3 rows are fetched together, longer rows (degree > 32) take a loop.
 // unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a reciprocal multiply.
+// `rp` = rowptr[first row of the warp + lane] for lanes 0..6, loaded by the caller ahead of time.
 template <int FMT>
-__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane)
+__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane, int rp)
 {
     const AggView& g = a.aggv;
-    const int r0 = n0 + 8 * wid;
-    int rp = 0;
-    if (lane < 9) rp = g.rowptr[min(r0 + lane, a.n_rows)];
+    const int r0 = n0 + ROWS_PER_WARP * wid;
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb) {
-        float4 f[4][2], f2[4][2];
-        int s_[4], e_[4];
+        float4 f[3][2], f2[3][2];
+        int s_[3], e_[3];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int row = r0 + 4 * hb + u;
-            s_[u] = __shfl_sync(0xffffffffu, rp, 4 * hb + u);
-            e_[u] = __shfl_sync(0xffffffffu, rp, 4 * hb + u + 1);
+        for (int u = 0; u < 3; ++u) {
+            const int row = r0 + 3 * hb + u;
+            s_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u);
+            e_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u + 1);
             if (row >= a.n_rows) e_[u] = s_[u];
             f[u][0] = f[u][1] = f2[u][0] = f2[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e_[u] > s_[u]) {
@@ -138,7 +139,7 @@ __device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 3; ++u) {
             float v[8] = {f[u][0].x + f2[u][0].x, f[u][0].y + f2[u][0].y, f[u][0].z + f2[u][0].z, f[u][0].w + f2[u][0].w,
                           f[u][1].x + f2[u][1].x, f[u][1].y + f2[u][1].y, f[u][1].z + f2[u][1].z, f[u][1].w + f2[u][1].w};
             if (e_[u] > s_[u]) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a
                 }
             }
             const float sc = g.mean ? __fdividef(1.0f, (float)max(e_[u] - s_[u], 1)) : g.inv_norm;
-            *reinterpret_cast<uint4*>(tile + chunk_offset(8 * wid + 4 * hb + u, lane, NX_PANEL)) =
+            *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + 3 * hb + u, lane, NX_PANEL)) =
                 make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
                            pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
         }
@@ -181,11 +182,14 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), COMPUTE_WARPS); }
         fence_barrier_init();
     }
-    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), 2 * ACC_COLS);
+    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), 512);          // 2 x 192 accumulator columns; allocations are powers of two
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_holder;
+    pdl_launch_dependents();
+    // Weights are launch-invariant: the TMA thread starts streaming them while the previous kernel drains
+    // (programmatic dependent launch); every warp that touches h / agg / pq waits for it first.
 
     if (wid == TMA_WARP) {
         // ================================ weight stream ================================
@@ -234,7 +238,9 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         }
     } else {
         // ================================ compute warps ================================
-        const int q = wid & 3, g = wid >> 2, half = g & 1, nh = g >> 1;
+        // epilogue mapping: warp = (TMEM lane quarter q, channel half, 48-column half of the tile);
+        // thread = one output channel, registers = 16 node columns per tcgen05.ld
+        const int q = wid & 3, g = wid >> 2, half = g >> 1, c0 = COLS_PER_WARP * (g & 1);
         const int ch = 128 * half + 32 * q + lane;
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
         int acc_uses[2] = {0, 0};
@@ -254,11 +260,15 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             if (lane == 0) mbar_arrive(smem_u32(&s.bar_x[which]));
         };
         const bool tr = wid == 0 && lane == 0;
+        pdl_wait();
         if (tr) trace_mark(a.trace, 0, 0, 0);
+        const int n_valid = a.n_rows - n0;                                          // rows of this tile that exist
         if (a.do_mlp) {
+            int rp = 0;                                                              // CSR bounds of the warp's rows: issued first
+            if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
             stage_h<FMT>(s.xa, a, n0, wid, lane);
             if (tr) trace_mark(a.trace, 0, 0, 1);
-            stage_agg<FMT>(s.xb, a, n0, wid, lane);
+            stage_agg<FMT>(s.xb, a, n0, wid, lane, rp);
             publish(0);
             if (tr) trace_mark(a.trace, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> xa (the n0 MMAs have all retired: acc_full follows them)
@@ -266,37 +276,41 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             wait_acc(0);
             if (tr) trace_mark(a.trace, 0, 0, 3);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                tmem_ld32(tmem_base + t_lane + half * NT + 64 * nh + 32 * pass, v);
+            for (int cc = 0; cc < 3; ++cc) {
+                float v[16];
+                const int i0 = c0 + 16 * cc;
+                tmem_ld16(tmem_base + t_lane + half * NT + i0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) store_k16<FMT>(s.xa, 64 * nh + 32 * pass + j, ch, silu_tc<FMT>(v[j] + b3c));
+                for (int j = 0; j < 16; ++j) store_k16<FMT>(s.xa, i0 + j, ch, silu_tc<FMT>(v[j] + b3c));
             }
             release_acc(0);
             publish(1);
             if (tr) trace_mark(a.trace, 0, 0, 4);
             // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> xb
             const float b4c = a.b4[ch];
-            float r[32];                                                             // residual rows of pass 0: fetched under the MMAs
+            float* hrow = a.h + (size_t)(n0 + c0) * H + ch;
+            float r[16];                                                             // residual rows of chunk 0: fetched under the MMAs
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = (n0 + 64 * nh + j < a.n_rows) ? a.h[(size_t)(n0 + 64 * nh + j) * H + ch] : 0.f;
+            for (int j = 0; j < 16; ++j) r[j] = (c0 + j < n_valid) ? hrow[(size_t)j * H] : 0.f;
             wait_acc(1);
             if (tr) trace_mark(a.trace, 0, 0, 5);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                const int i0 = 64 * nh + 32 * pass;
-                if (pass == 1) {
+            for (int cc = 0; cc < 3; ++cc) {
+                float v[16], rn[16];
+                const int i0 = c0 + 16 * cc;
+                tmem_ld16(tmem_base + ACC_COLS + t_lane + half * NT + i0, v);
+                if (cc < 2) {                                                        // next chunk's residual rows
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = (n0 + i0 + j < a.n_rows) ? a.h[(size_t)(n0 + i0 + j) * H + ch] : 0.f;
+                    for (int j = 0; j < 16; ++j) rn[j] = (i0 + 16 + j < n_valid) ? hrow[(size_t)(16 * cc + 16 + j) * H] : 0.f;
                 }
-                tmem_ld32(tmem_base + ACC_COLS + t_lane + half * NT + i0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const float o = r[j] + (v[j] + b4c);
-                    if (n0 + i0 + j < a.n_rows) a.h[(size_t)(n0 + i0 + j) * H + ch] = o;
-                    store_k16<FMT>(s.xb, i0 + j, ch, (n0 + i0 + j < a.n_rows) ? o : 0.f);
+                    if (i0 + j < n_valid) hrow[(size_t)(16 * cc + j) * H] = o;
+                    store_k16<FMT>(s.xb, i0 + j, ch, (i0 + j < n_valid) ? o : 0.f);
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = rn[j];
             }
             release_acc(1);
             publish(2);
@@ -309,25 +323,26 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         for (int b = 0; b < a.n_blocks; ++b) {
             const int acc = b & 1;
             const float bias = a.bp[b * 256 + ch];
-            float* dst = a.pq + (size_t)b * 256 + ch;
+            float* dst = a.pq + (size_t)(n0 + c0) * a.ldp + (size_t)b * 256 + ch;
             wait_acc(acc);
-            if (tr) trace_mark(a.trace, 0, 0, 7 + 2 * b);
+            if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                float v[32];
-                const int i0 = 64 * nh + 32 * pass;
-                tmem_ld32(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
-                if (pass == 1) release_acc(acc);
+            for (int cc = 0; cc < 3; ++cc) {
+                float v[16];
+                const int i0 = c0 + 16 * cc;
+                tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
+                if (cc == 2) release_acc(acc);
+                float* d = dst + (size_t)(16 * cc) * a.ldp;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (n0 + i0 + j < a.n_rows) dst[(size_t)(n0 + i0 + j) * a.ldp] = v[j] + bias;
+                for (int j = 0; j < 16; ++j, d += a.ldp)
+                    if (i0 + j < n_valid) *d = v[j] + bias;
             }
-            if (tr) trace_mark(a.trace, 0, 0, 8 + 2 * b);
+            if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (wid == MMA_WARP) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    if (wid == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -359,8 +374,9 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     if (p.N <= 0) return DP_OK;
     const int grid = (p.N + NT - 1) / NT;
     const int smem = (int)sizeof(NodeSmem) + 1024;
-    if (fmt == tc::FMT_BF16) node_tc_kernel<tc::FMT_BF16><<<grid, THREADS, smem, st>>>(a, h->tc->node[v].img[fmt]);
-    else node_tc_kernel<tc::FMT_F16><<<grid, THREADS, smem, st>>>(a, h->tc->node[v].img[fmt]);
+    const unsigned char* img = h->tc->node[v].img[fmt];
+    if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    else DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_F16>, dim3(grid), dim3(THREADS), smem, st, a, img));
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
