@@ -57,7 +57,10 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{idx}"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+    his = [i for i, r in enumerate(rows) if r and r[0].strip() == "Address"]
+    if not his:
+        raise SystemExit("no source table in the report output:\n" + out[:400])
+    hi = his[0]
     hdr = rows[hi]
     print("#", rows[0][1] if len(rows[0]) > 1 else "")
     ci = {h: i for i, h in enumerate(hdr)}
