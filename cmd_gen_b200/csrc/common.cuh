@@ -9,7 +9,7 @@
 constexpr int H = 256;            // hidden_nf (compile-time tile width)
 constexpr int UNIT_F32 = 64;      // edges per segmented-sum unit, FFMA path
 constexpr int UNIT_TC = 32;       // edges per segmented-sum unit, tcgen05 path
-constexpr int DP_TRACE_WORDS = 3 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
+constexpr int DP_TRACE_WORDS = 4 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
 
 void dp_set_error(const char* fmt, ...);
 

@@ -14,8 +14,11 @@
 // no atomics, no shuffles — and agg stores are 128 B coalesced.
 //
 // Warp-specialised, persistent (one CTA per SM, tiles round-robin):
-//   warps 0-7   epilogue : TMEM -> registers, SiLU, gate (smem-transposed reduce over the 256 channels),
-//                          segmented sum, stores.  warp w reads TMEM lanes 32 (w % 4) .. +32.
+//   warps 0-7   epilogue : two independent groups of 4 warps; group g owns the g-th 32-edge unit of every tile.
+//                          Warp (g, q) reads TMEM lanes 32 q .. +32 of BOTH accumulator halves, so a thread
+//                          holds channels c and c + 128 for 32 edges: SiLU, gate (in-thread pre-add of the two
+//                          channels, one smem-transposed reduce per warp, 4-warp named barrier per group),
+//                          segmented sum as two independent FMA chains, stores.
 //   warps 8-15  producer : each warp owns 8 edges of the tile: gathers the pre-projected rows (Pa once per
 //                          CSR row run, Pb per edge; 128-bit loads, 8 in flight per lane), first layer,
 //                          writes the swizzled K-major B tile, fence.proxy.async, arrives on full[stage].
@@ -40,14 +43,14 @@ constexpr int MMA_WARP = EPI_WARPS + PRO_WARPS;
 constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 5 warpgroups: 2 epilogue, 2 producer, 1 MMA (+3 idle warps)
 // Registers are allocated per SM sub-partition (16384 each, 5 warps per sub-partition here), so the launch
 // gets 96 per thread; setmaxnreg then moves the idle warpgroup's share to the producers.
-constexpr int REGS_MMA = 40, REGS_PRODUCER = 120;
-constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer
+constexpr int REGS_MMA = 40, REGS_PRODUCER = 120, REGS_EPILOGUE = 96;    // 2 Re + 2 Rp + Rm <= 5 x 96: the CTA pool only holds what its own warps released
+constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer (16 edges + pad)
 
 struct EdgeSmem {                                 // offsets from a 1024-aligned base
     unsigned char w[4 * W_PANEL_BYTES];           // 128 KB resident second-layer weights
     unsigned char x[N_XS][X_TILE_BYTES];          // 64 KB
-    float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel][16 edges (+4 pad)]
-    float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over units
+    float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel pair][16 edges (+4 pad)]
+    float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][32];
     unsigned long long bar_w;
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
@@ -79,12 +82,14 @@ __device__ __forceinline__ void unpack8(const float4& a, const float4& b, float 
 }
 
 // debug timeline: role 0 = producer warp 0, 1 = MMA thread, 2 = epilogue warp 0; CTA 0 only
-__device__ __forceinline__ void trace_mark(long long* trace, int role, int it, int slot)
+template <bool TRACE>
+__device__ __forceinline__ void trace_mark_t(long long* trace, int role, int it, int slot)
 {
-    if (trace && blockIdx.x == 0 && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64();
+    if (TRACE) { if (blockIdx.x == 0 && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64(); }
 }
+#define trace_mark(tr, role, it, slot) trace_mark_t<TRACE>(tr, role, it, slot)
 
-template <int FMT>
+template <int FMT, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const unsigned char* __restrict__ w_img)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -243,107 +248,117 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         }
     } else {
         // ================================ epilogue ================================
-        const int ew = wid, q = ew & 3, half = ew >> 2;
-        const int ch = 128 * half + 32 * q + lane;
-        const float b2c = a.b2[ch];
+        static_assert(REGS_EPILOGUE == 96, "the epilogue keeps its launch allocation");
+        const int ew = wid, q = ew & 3, gi = ew >> 2;
+        const int c0 = 32 * q + lane, c1 = c0 + 128;                                     // this thread's two channels
+        const float b2_0 = a.b2[c0], b2_1 = a.b2[c1];
         const bool gated = a.coord || a.attention;
-        const float wvc = gated ? a.wv[ch] : 0.f;
+        const float wv0 = gated ? a.wv[c0] : 0.f, wv1 = gated ? a.wv[c1] : 0.f;
         static_assert(H == 256, "segment stores shift by 8");
-        float* out_ch = a.agg + ch;                                                      // [agg rows | partial rows], see graph.cu edge_dst
+        float* out0 = a.agg + c0;                                                        // [agg rows | partial rows], see graph.cu edge_dst
+        float* out1 = a.agg + c1;
         float* redw = s.red[ew];
-        const int g = lane >> 4, l16 = lane & 15;
-        int unit_no = 0;
+        float* gatew = s.gate[ew];
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
             const int tile = blockIdx.x + it * gridDim.x;
-            const int e0 = tile * TILE;
-            const int dst0 = (!a.coord && e0 + lane < E) ? a.edst[e0 + lane] : -1;
-            const int dst1 = (!a.coord && e0 + 32 + lane < E) ? a.edst[e0 + 32 + lane] : -1;
-            if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 0);
+            const int u0 = tile * TILE + 32 * gi;                                        // first edge of this group's unit
+            const int my_dst = (!a.coord && u0 + lane < E) ? a.edst[u0 + lane] : -1;
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
             mbar_wait(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
-            if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 1);
-#pragma unroll 1
-            for (int un = 0; un < 2; ++un, ++unit_no) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + ts * TS_COLS + half * TILE + un * 32, v);
-                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 2 + 7 * un);
-                if (un == 1) {                                                          // accumulator stage drained
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
-                }
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 1);
+            float v0[32], v1[32];
+            {
+                uint32_t r0[32], r1[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + ts * TS_COLS + 32 * gi;
+                tmem_ld32_issue(taddr, r0);
+                tmem_ld32_issue(taddr + TILE, r1);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = silu_tc<FMT>(v[j] + b2c);
-                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 3 + 7 * un);
-                const int u0 = e0 + 32 * un;                                             // first edge of this 32-edge unit
-                float gate = 1.f;
-                if (gated) {
-                    // sum over the 256 channels of wv[c] * m[c, edge]: per warp a transposed reduce through
-                    // shared memory (thread = channel writes rows, thread = edge sums columns), then 8 warps
-                    float tot2[2];
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const int j = 16 * hh + 4 * j4;
-                            *reinterpret_cast<float4*>(redw + lane * RED_STRIDE + 4 * j4) =
-                                make_float4(wvc * v[j], wvc * v[j + 1], wvc * v[j + 2], wvc * v[j + 3]);
-                        }
-                        __syncwarp();
-                        float t = 0.f;
-#pragma unroll
-                        for (int kk = 0; kk < 16; ++kk) {
-                            const int k = (kk & 3) + 8 * (kk >> 2) + 4 * g;              // bank-conflict-free split of the 32 channels
-                            t += redw[k * RED_STRIDE + l16];
-                        }
-                        t += __shfl_xor_sync(0xffffffffu, t, 16);
-                        tot2[hh] = t;
-                        __syncwarp();
-                    }
-                    const int pbuf = unit_no & 1;
-                    s.part[pbuf][ew][lane] = g ? tot2[1] : tot2[0];                      // lane = edge inside the unit
-                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 4 + 7 * un);
-                    named_bar_sync(1, EPI_WARPS * 32);
-                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 5 + 7 * un);
-                    float tot = a.bv;
-#pragma unroll
-                    for (int k = 0; k < EPI_WARPS; ++k) tot += s.part[pbuf][k][lane];
-                    if (a.coord) gate = a.use_tanh ? tanhf(tot) : tot;                   // egnn_new.py:90-93
-                    else gate = sigmoid_fast(tot);                                       // egnn_new.py:26-29
-                }
-                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 6 + 7 * un);
-                if (a.coord) {
-                    if (ew == 0 && u0 + lane < E) a.escal[u0 + lane] = gate;
-                } else {
-                    // segmented sum over this unit's edges: thread = channel, registers = edges
-                    float gj[32];
-                    if (gated) {
-                        s.gate[ew][lane] = gate;
-                        __syncwarp();
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 t = *reinterpret_cast<const float4*>(&s.gate[ew][4 * j4]);
-                            gj[4 * j4] = t.x; gj[4 * j4 + 1] = t.y; gj[4 * j4 + 2] = t.z; gj[4 * j4 + 3] = t.w;
-                        }
-                        __syncwarp();
-                    }
-                    if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 7 + 7 * un);
-                    const int my_dst = un ? dst1 : dst0;
-                    const unsigned last_mask = __ballot_sync(0xffffffffu, my_dst >= 0);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        sum = gated ? fmaf(gj[j], v[j], sum) : sum + v[j];
-                        if (last_mask & (1u << j)) {                                     // warp-uniform
-                            const unsigned d = (unsigned)__shfl_sync(0xffffffffu, my_dst, j);
-                            out_ch[(size_t)d << 8] = sum;                                // row d of [agg | partials], H = 256
-                            sum = 0.f;
-                        }
-                    }
-                }
-                if (ew == 0 && lane == 0) trace_mark(a.trace, 2, it, 8 + 7 * un);
+                for (int j = 0; j < 32; ++j) { v0[j] = __uint_as_float(r0[j]); v1[j] = __uint_as_float(r1[j]); }
             }
+            tc_fence_before();                                                           // this warp's share of the stage is drained
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v0[j] = silu_tc<FMT>(v0[j] + b2_0); v1[j] = silu_tc<FMT>(v1[j] + b2_1); }
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 3);
+            float gate = 1.f;
+            if (gated) {
+                // sum over the 256 channels of wv[c] * m[c, edge]: the thread's two channels are added in
+                // registers, the warp's 32 lanes through a transposed pass over shared memory (thread = channel
+                // pair writes a row, thread = edge sums a column), the group's 4 warps through s.part
+                const int g = lane >> 4, l16 = lane & 15;
+                float tot2[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const int j = 16 * hh + 4 * j4;
+                        *reinterpret_cast<float4*>(redw + lane * RED_STRIDE + 4 * j4) =
+                            make_float4(fmaf(wv1, v1[j], wv0 * v0[j]), fmaf(wv1, v1[j + 1], wv0 * v0[j + 1]),
+                                        fmaf(wv1, v1[j + 2], wv0 * v0[j + 2]), fmaf(wv1, v1[j + 3], wv0 * v0[j + 3]));
+                    }
+                    __syncwarp();
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {                                     // bank-conflict-free split of the 32 rows
+                        const int k = 8 * kk + 4 * g;
+                        t0 += redw[k * RED_STRIDE + l16];
+                        t1 += redw[(k + 1) * RED_STRIDE + l16];
+                        t2 += redw[(k + 2) * RED_STRIDE + l16];
+                        t3 += redw[(k + 3) * RED_STRIDE + l16];
+                    }
+                    float t = (t0 + t1) + (t2 + t3);
+                    t += __shfl_xor_sync(0xffffffffu, t, 16);
+                    tot2[hh] = t;
+                    __syncwarp();
+                }
+                const int pbuf = it & 1;
+                s.part[pbuf][ew][lane] = g ? tot2[1] : tot2[0];                             // lane = edge inside the unit
+                if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 4);
+                named_bar_sync(1 + gi, 4 * 32);
+                if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 5);
+                const float tot = a.bv + ((s.part[pbuf][4 * gi][lane] + s.part[pbuf][4 * gi + 1][lane]) +
+                                          (s.part[pbuf][4 * gi + 2][lane] + s.part[pbuf][4 * gi + 3][lane]));
+                if (a.coord) gate = a.use_tanh ? tanhf(tot) : tot;                       // egnn_new.py:90-93
+                else gate = sigmoid_fast(tot);                                           // egnn_new.py:26-29
+            }
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 6);
+            if (a.coord) {
+                if (q == 0 && u0 + lane < E) a.escal[u0 + lane] = gate;
+            } else {
+                // segmented sum over the unit's edges: thread = channel pair, registers = edges (two FMA chains)
+                if (gated) {
+                    gatew[lane] = gate;
+                    __syncwarp();
+                }
+                const unsigned last_mask = __ballot_sync(0xffffffffu, my_dst >= 0);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float gq[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (gated) {
+                        const float4 t = *reinterpret_cast<const float4*>(gatew + 4 * j4);
+                        gq[0] = t.x; gq[1] = t.y; gq[2] = t.z; gq[3] = t.w;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * j4 + jj;
+                        s0 = fmaf(gq[jj], v0[j], s0);
+                        s1 = fmaf(gq[jj], v1[j], s1);
+                        if (last_mask & (1u << j)) {                                     // warp-uniform
+                            const size_t d = (size_t)(unsigned)__shfl_sync(0xffffffffu, my_dst, j) << 8;   // row d of [agg | partials], H = 256
+                            out0[d] = s0; out1[d] = s1;
+                            s0 = 0.f; s1 = 0.f;
+                        }
+                    }
+                }
+                __syncwarp();                                                            // gatew / redw are rewritten next tile
+            }
+            if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 7);
         }
     }
     tc_fence_before();
@@ -356,8 +371,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 int tc_edge_init()
 {
     static_assert(sizeof(EdgeSmem) + 1024 <= 232448, "edge kernel shared memory exceeds 227 KB");
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem) + 1024));
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem) + 1024));
+    const int smem = (int)sizeof(EdgeSmem) + 1024;
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return DP_OK;
 }
 
@@ -372,8 +390,13 @@ int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
     const int smem = (int)sizeof(EdgeSmem) + 1024;
     const int grid = h->sm_count;
     const unsigned char* img = L.img[fmt];
-    if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
-    else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    if (a.trace) {
+        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16, true>, dim3(grid), dim3(THREADS), smem, st, a, img));
+        else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16, true>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    } else {
+        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
+        else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    }
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;

@@ -27,22 +27,22 @@ t = torch.full((B,), 0.4)
 for _ in range(3):
     h.dynamics_forward(z, xr, t)
 torch.cuda.synchronize()
-n = 3 * 64 * 16
+n = 4 * 64 * 16
 buf = (C.c_longlong * n)()
 h.lib.dp_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
 rc = h.lib.dp_debug_trace(h.h, buf, n)
 assert rc == 0, h.lib.dp_last_error()
-tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(3)]
+tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(4)]
 t0 = min(v for r in tr for it in r for v in it if v > 0)
 names = {0: ["start", "xempty", "b0 issued", "b0 done", "b1 issued", "b1 done", "arrive"],
          1: ["start", "full", "tempty", "issued"],
-         2: ["start", "tfull", "ld0", "silu0", "red0", "bar0", "gate0", "bcast0", "seg0",
-             "ld1", "silu1", "red1", "bar1", "gate1", "bcast1", "seg1"]}
+         2: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"],
+         3: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"]}
 print("E =", h.flags().last_n_edges, " (cycles relative to the first mark, CTA 0)")
 w = tr[1][63]
 print(f"weights: issue {w[0] - t0}  landed {w[1] - t0}")
 for it in range(10):
-    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue")):
+    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue0"), (3, "epilogue1")):
         row = tr[r][it]
         if not any(row):
             continue
