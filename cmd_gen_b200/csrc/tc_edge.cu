@@ -24,9 +24,10 @@
 //                          writes the swizzled K-major B tile, fence.proxy.async, arrives on full[stage].
 //   warp  16    MMA      : (warps 17-19 idle: they only donate their registers, setmaxnreg) one thread waits full[stage] / tmem_empty[acc], issues 32 tcgen05.mma
 //                          (M=128, N=64, K=16) per tile and commits to x_empty[stage] + tmem_full[acc].
-// Second-layer weights (128 KB swizzled bf16/f16 image) stay resident in shared memory for the whole
-// kernel, fetched once per CTA with cp.async.bulk.  2 activation stages x 32 KB, 4 accumulator stages
-// x 128 TMEM columns.
+// Second-layer weights are the A operand and stay resident in TENSOR MEMORY for the whole kernel (256
+// columns: 2 M-halves x 128 columns of packed 16-bit pairs, written once per CTA by the epilogue warps with
+// tcgen05.st), so an MMA reads only its 2 KB B tile from shared memory (the SS form read 6 KB: the
+// shared-memory port was the MMA's limit).  4 activation stages x 32 KB, 2 accumulator stages x 128 columns.
 #include "tc_common.cuh"
 
 namespace {
@@ -35,9 +36,11 @@ using namespace tc;
 constexpr int TILE = 64;                          // edges per tile (UMMA N)
 constexpr int X_PANEL_BYTES = TILE * 128;         // 8 KB
 constexpr int X_TILE_BYTES = 4 * X_PANEL_BYTES;   // 32 KB: 64 edges x 256 K x 2 B
-constexpr int N_XS = 2;                           // activation stages
-constexpr int N_TS = 4;                           // accumulator stages
+constexpr int N_XS = 4;                           // activation stages
+constexpr int N_TS = 2;                           // accumulator stages
 constexpr int TS_COLS = 2 * TILE;                 // TMEM columns per accumulator stage
+constexpr int W_COLS = 256;                       // TMEM columns of the resident weights: half hh at hh * 128, K pair j at column j
+constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8, PRO_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + PRO_WARPS;
 constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 5 warpgroups: 2 epilogue, 2 producer, 1 MMA (+3 idle warps)
@@ -47,8 +50,7 @@ constexpr int REGS_MMA = 40, REGS_PRODUCER = 120, REGS_EPILOGUE = 96;    // 2 Re
 constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer (16 edges + pad)
 
 struct EdgeSmem {                                 // offsets from a 1024-aligned base
-    unsigned char w[4 * W_PANEL_BYTES];           // 128 KB resident second-layer weights
-    unsigned char x[N_XS][X_TILE_BYTES];          // 64 KB
+    unsigned char x[N_XS][X_TILE_BYTES];          // 128 KB
     float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel pair][16 edges (+4 pad)]
     float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][32];
@@ -58,8 +60,8 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     uint32_t tmem_holder;
 };
 
-// D[256 x 64] = W[256 x 256] * X[64 x 256]^T  as 2 (M halves) x 4 (panels) x 4 (K steps) MMAs
-__device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t w_base, uint32_t x_base, uint32_t idesc)
+// D[256 x 64] = W[256 x 256] * X[64 x 256]^T  as 2 (M halves) x 4 (panels) x 4 (K steps) MMAs, A from TMEM
+__device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t tmem_w, uint32_t x_base, uint32_t idesc)
 {
 #pragma unroll
     for (int kp = 0; kp < 4; ++kp) {
@@ -68,10 +70,8 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t w_base,
             const uint64_t bdesc = make_desc(x_base + kp * X_PANEL_BYTES + ks * 32);
             const uint32_t acc = (kp > 0 || ks > 0) ? 1u : 0u;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const uint64_t adesc = make_desc(w_base + kp * W_PANEL_BYTES + hh * (128 * 128) + ks * 32);
-                umma_f16(tmem_d + hh * TILE, adesc, bdesc, idesc, acc);
-            }
+            for (int hh = 0; hh < 2; ++hh)
+                umma_f16_ts(tmem_d + hh * TILE, tmem_w + hh * 128 + kp * 32 + ks * 8, bdesc, idesc, acc);
         }
     }
 }
@@ -99,22 +99,18 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 
     // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
     if (tid == 0) {
-        mbar_init(smem_u32(&s.bar_w), 1);
+        mbar_init(smem_u32(&s.bar_w), EPI_WARPS);
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
         for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
         fence_barrier_init();
     }
-    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), N_TS * TS_COLS);
+    if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = s.tmem_holder;
-    if (wid == MMA_WARP && lane == 0) {
-        const uint32_t bar_w = smem_u32(&s.bar_w);
-        mbar_expect_tx(bar_w, 4 * W_PANEL_BYTES);
-        for (int p = 0; p < 4; ++p)
-            bulk_g2s(smem_u32(s.w + p * W_PANEL_BYTES), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, bar_w);
-    }
+    const uint32_t tmem_w = s.tmem_holder;                   // resident weights
+    const uint32_t tmem_base = tmem_w + W_COLS;              // accumulator stages
+    static_assert(W_COLS + N_TS * TS_COLS <= TMEM_COLS, "tensor memory budget");
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     const int E = *a.n_edges;
@@ -128,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const uint32_t bar_w = smem_u32(&s.bar_w);
             constexpr uint32_t idesc = make_idesc(FMT, 128, TILE);
             trace_mark(a.trace, 1, 63, 0);
-            mbar_wait(bar_w, 0);
+            if (my_tiles > 0) mbar_wait(bar_w, 0);                     // weights are in tensor memory
             trace_mark(a.trace, 1, 63, 1);
             for (int it = 0; it < my_tiles; ++it) {
                 const int xs = it % N_XS, ts = it % N_TS;
@@ -138,7 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 mbar_wait(smem_u32(&s.bar_tempty[ts]), ((it / N_TS) & 1) ^ 1);
                 trace_mark(a.trace, 1, it, 2);
                 tc_fence_after();
-                issue_tile_mma(tmem_base + ts * TS_COLS, smem_u32(s.w), smem_u32(s.x[xs]), idesc);
+                issue_tile_mma(tmem_base + ts * TS_COLS, tmem_w, smem_u32(s.x[xs]), idesc);
                 umma_commit(smem_u32(&s.bar_xempty[xs]));
                 umma_commit(smem_u32(&s.bar_tfull[ts]));
                 trace_mark(a.trace, 1, it, 3);
@@ -259,6 +255,27 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* out1 = a.agg + c1;
         float* redw = s.red[ew];
         float* gatew = s.gate[ew];
+        if (my_tiles > 0) {
+            // resident weights: thread (q, lane) of group gi owns row c = 128 gi + 32 q + lane of the [out][in]
+            // matrix = TMEM lane 32 q + lane of M-half gi.  Its 256 K elements are read from the swizzled panel
+            // image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 128 packed 32-bit columns.
+            const int r = 128 * gi + 32 * q + lane;
+#pragma unroll 1
+            for (int kp = 0; kp < 4; ++kp) {
+                const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
+                uint32_t wreg[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
+                    wreg[4 * c] = t.x; wreg[4 * c + 1] = t.y; wreg[4 * c + 2] = t.z; wreg[4 * c + 3] = t.w;
+                }
+                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32, wreg);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.bar_w));
+        }
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
             const int tile = blockIdx.x + it * gridDim.x;
@@ -363,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     }
     tc_fence_before();
     __syncthreads();
-    if (wid == MMA_WARP) tmem_dealloc(tmem_base, N_TS * TS_COLS);
+    if (wid == MMA_WARP) tmem_dealloc(tmem_w, TMEM_COLS);
 }
 
 }  // namespace
