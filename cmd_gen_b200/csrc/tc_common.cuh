@@ -50,6 +50,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of a converged warp (the tcgen05 / TMA issue idiom: the WHOLE warp runs the role's control flow so
+// addresses and descriptors stay in uniform registers; a lane-0 branch makes the compiler wrap every
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, ~90 cycles per issue)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- bulk copy global -> shared (TMA engine, 1-D) ---------------------------------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {

@@ -120,24 +120,30 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     if (wid >= MMA_WARP) {
         // ================================ MMA issuer ================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
-        if (wid == MMA_WARP && lane == 0) {
+        if (wid == MMA_WARP) {
+            // the whole warp runs the loop (uniform control flow); one elected lane issues
             const uint32_t bar_w = smem_u32(&s.bar_w);
             constexpr uint32_t idesc = make_idesc(FMT, 128, TILE);
-            trace_mark(a.trace, 1, 63, 0);
+            const uint32_t tw = warp_uniform(tmem_w), td = warp_uniform(tmem_base);
+            const uint32_t x0 = warp_uniform(smem_u32(s.x[0]));
+            if (lane == 0) trace_mark(a.trace, 1, 63, 0);
             if (my_tiles > 0) mbar_wait(bar_w, 0);                     // weights are in tensor memory
-            trace_mark(a.trace, 1, 63, 1);
+            if (lane == 0) trace_mark(a.trace, 1, 63, 1);
             for (int it = 0; it < my_tiles; ++it) {
                 const int xs = it % N_XS, ts = it % N_TS;
-                trace_mark(a.trace, 1, it, 0);
+                if (lane == 0) trace_mark(a.trace, 1, it, 0);
                 mbar_wait(smem_u32(&s.bar_full[xs]), (it / N_XS) & 1);
-                trace_mark(a.trace, 1, it, 1);
+                if (lane == 0) trace_mark(a.trace, 1, it, 1);
                 mbar_wait(smem_u32(&s.bar_tempty[ts]), ((it / N_TS) & 1) ^ 1);
-                trace_mark(a.trace, 1, it, 2);
+                if (lane == 0) trace_mark(a.trace, 1, it, 2);
                 tc_fence_after();
-                issue_tile_mma(tmem_base + ts * TS_COLS, tmem_w, smem_u32(s.x[xs]), idesc);
-                umma_commit(smem_u32(&s.bar_xempty[xs]));
-                umma_commit(smem_u32(&s.bar_tfull[ts]));
-                trace_mark(a.trace, 1, it, 3);
+                if (elect_one()) {
+                    issue_tile_mma(td + ts * TS_COLS, tw, x0 + xs * X_TILE_BYTES, idesc);
+                    umma_commit(smem_u32(&s.bar_xempty[xs]));
+                    umma_commit(smem_u32(&s.bar_tfull[ts]));
+                }
+                __syncwarp();
+                if (lane == 0) trace_mark(a.trace, 1, it, 3);
             }
         }
     } else if (wid >= EPI_WARPS) {

@@ -193,20 +193,29 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
 
     if (wid == TMA_WARP) {
         // ================================ weight stream ================================
-        if (lane == 0) {
+        {
+            const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
             for (int p = 0; p < n_panels; ++p) {
                 const int slot = p % N_WS;
-                trace_mark(a.trace, 2, p, 0);
+                if (lane == 0) trace_mark(a.trace, 2, p, 0);
                 mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS) & 1) ^ 1);
-                trace_mark(a.trace, 2, p, 1);
-                mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_PANEL_BYTES);
-                bulk_g2s(smem_u32(s.w[slot]), w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
+                if (lane == 0) trace_mark(a.trace, 2, p, 1);
+                if (elect_one()) {
+                    mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_PANEL_BYTES);
+                    bulk_g2s(w0 + slot * W_PANEL_BYTES, w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
+                }
+                __syncwarp();
             }
         }
     } else if (wid == MMA_WARP) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // the whole warp runs the control flow (uniform: descriptors stay in uniform registers), one elected lane issues
+        {
             constexpr uint32_t idesc = make_idesc(FMT, 128, NT);
+            const uint32_t td = warp_uniform(tmem_base);
+            const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
+            const uint32_t xa = warp_uniform(smem_u32(s.xa)), xb = warp_uniform(smem_u32(s.xb));
+            const bool tr = lane == 0;
             int p = 0;
             int acc_uses[2] = {0, 0};
             auto run_gemm = [&](int acc, uint32_t x0, uint32_t x1, int k_panels) {
@@ -215,26 +224,29 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 tc_fence_after();
                 for (int kp = 0; kp < k_panels; ++kp, ++p) {
                     const int slot = p % N_WS;
-                    trace_mark(a.trace, 1, p, 0);
+                    if (tr) trace_mark(a.trace, 1, p, 0);
                     mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS) & 1);
-                    trace_mark(a.trace, 1, p, 1);
+                    if (tr) trace_mark(a.trace, 1, p, 1);
                     tc_fence_after();
                     const uint32_t xp = (kp < 4 ? x0 + kp * NX_PANEL : x1 + (kp - 4) * NX_PANEL);
-                    issue_panel(tmem_base + acc * ACC_COLS, smem_u32(s.w[slot]), xp, idesc, kp == 0);
-                    umma_commit(smem_u32(&s.bar_wempty[slot]));
-                    trace_mark(a.trace, 1, p, 2);
+                    if (elect_one()) {
+                        issue_panel(td + acc * ACC_COLS, w0 + slot * W_PANEL_BYTES, xp, idesc, kp == 0);
+                        umma_commit(smem_u32(&s.bar_wempty[slot]));
+                        if (kp == k_panels - 1) umma_commit(smem_u32(&s.bar_accfull[acc]));
+                    }
+                    __syncwarp();
+                    if (tr) trace_mark(a.trace, 1, p, 2);
                 }
-                umma_commit(smem_u32(&s.bar_accfull[acc]));
                 acc_uses[acc] += 1;
             };
             if (a.do_mlp) {
                 mbar_wait(smem_u32(&s.bar_x[0]), 0);
-                run_gemm(0, smem_u32(s.xa), smem_u32(s.xb), 8);
+                run_gemm(0, xa, xb, 8);
                 mbar_wait(smem_u32(&s.bar_x[1]), 0);
-                run_gemm(1, smem_u32(s.xa), 0, 4);
+                run_gemm(1, xa, 0, 4);
             }
             mbar_wait(smem_u32(&s.bar_x[2]), 0);
-            for (int b = 0; b < a.n_blocks; ++b) run_gemm(b & 1, smem_u32(s.xb), 0, 4);
+            for (int b = 0; b < a.n_blocks; ++b) run_gemm(b & 1, xb, 0, 4);
         }
     } else {
         // ================================ compute warps ================================
