@@ -106,7 +106,11 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     h->device = device;
     h->precision = cfg->precision;
     DP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (const char* m = getenv("DIFFPHAR_TC_MASK")) h->tc_mask = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_TC_MASK")) {
+        // debug switch: 3 = tcgen05 edge + node kernels (default), 0 = FFMA kernels even in the 16-bit modes.
+        // Mixed settings are not meaningful: the tensor-core path keeps pq pre-scaled by 1/2.
+        h->tc_mask = atoi(m) ? 3 : 0;
+    }
     if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
@@ -293,8 +297,14 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
         }
         if ((rc = upload(bag, &ps.lin.wt, wt))) return rc;
         if ((rc = upload(bag, &ps.lin.b, bias))) return rc;
+        // tensor-core image: weights and bias scaled by 1/2 (exact in every format), so the edge kernels get
+        // hv = x / 2 of the factored first layer without a multiply (tc_edge.cu)
+        std::vector<float> bias_half(bias);
+        for (float& b : bias_half) b *= 0.5f;
+        if ((rc = upload(bag, &ps.b_half, bias_half))) return rc;
         HostLinear& TL = h->tc_host[4 * G + c.n_layers + v];
         TL.K = H; TL.n_out = n_out; TL.wt = wt;
+        for (float& w : TL.wt) w *= 0.5f;
     }
     if ((rc = tc_prepare_weights(h))) return rc;
     h->tc_host.clear();

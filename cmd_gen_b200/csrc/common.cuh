@@ -122,6 +122,7 @@ struct CoordWeights {
 // A projection set: one GEMM h[N,H] -> PQ[N, n_out] feeding the next edge kernels.
 struct ProjSet {
     DevLinear lin;          // in = H, out = 512 or 1024
+    float* b_half = nullptr; // 0.5 * bias: the tcgen05 path keeps pq pre-scaled by 1/2 (SiLU(x) = hv + hv tanh(hv), hv = x / 2)
     int off_gcl = -1;       // column offset of (Pa|Pb) for the next GCL, -1 if none
     int off_coord = -1;     // column offset of (Qa|Qb) for the coordinate update, -1 if none
 };

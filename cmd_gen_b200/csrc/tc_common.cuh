@@ -165,6 +165,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
+// 128-bit global load that does not allocate in L1 (rows used once per warp; keeps L1 for the reused Pa rows).
+// Not volatile: the source is read-only for the whole launch, the scheduler may move the load freely.
+__device__ __forceinline__ float4 ldg_na(const float* p)
+{
+    float4 v;
+    asm("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+// 32 bytes (8 floats) reloaded only when `take` is set: predicated loads straight into the live registers,
+// no branch (keeps the caller's loop one basic block, so independent edges interleave)
+__device__ __forceinline__ void ldg8_if(float (&v)[8], const float* p, bool take)
+{
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %9, 0;\n"
+        "@q ld.global.v4.f32 {%0, %1, %2, %3}, [%8];\n"
+        "@q ld.global.v4.f32 {%4, %5, %6, %7}, [%8+16];\n"
+        "}" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+            : "l"(p), "r"((int)take));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -231,6 +255,15 @@ __device__ __forceinline__ float silu_tc(float v)
     } else {
         return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v));
     }
+}
+// SiLU(2 hv) from the HALVED pre-activation hv (the halving is folded into the preceding FMA's constants):
+//   FMT_BF16: hv + hv tanh(hv)                              -> MUFU + FFMA
+//   FMT_F16 : hv / (0.5 + 0.5 * 2^(-2 log2e hv))            -> FMUL, MUFU, FFMA, MUFU, FMUL
+template <int FMT>
+__device__ __forceinline__ float silu_half(float hv)
+{
+    if (FMT == FMT_BF16) return fmaf(hv, tanh_approx(hv), hv);
+    return hv * rcp_approx(fmaf(0.5f, ex2_approx(-2.8853900817779268f * hv), 0.5f));
 }
 __device__ __forceinline__ float sigmoid_fast(float v) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
 

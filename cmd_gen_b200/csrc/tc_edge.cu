@@ -46,7 +46,7 @@ constexpr int MMA_WARP = EPI_WARPS + PRO_WARPS;
 constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 5 warpgroups: 2 epilogue, 2 producer, 1 MMA (+3 idle warps)
 // Registers are allocated per SM sub-partition (16384 each, 5 warps per sub-partition here), so the launch
 // gets 96 per thread; setmaxnreg then moves the idle warpgroup's share to the producers.
-constexpr int REGS_MMA = 40, REGS_PRODUCER = 120, REGS_EPILOGUE = 96;    // 2 Re + 2 Rp + Rm <= 5 x 96: the CTA pool only holds what its own warps released
+constexpr int REGS_MMA = 32, REGS_PRODUCER = 120, REGS_EPILOGUE = 96;    // 2 Re + 2 Rp + Rm <= 5 x 96: the CTA pool only holds what its own warps released
 constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer (16 edges + pad)
 
 struct EdgeSmem {                                 // offsets from a 1024-aligned base
@@ -54,6 +54,7 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel pair][16 edges (+4 pad)]
     float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][32];
+    float touch[PRO_WARPS][32];                   // cp.async landing pad of the L1 row prefetch (never read)
     unsigned long long bar_w;
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
     unsigned long long bar_tfull[N_TS], bar_tempty[N_TS];
@@ -148,112 +149,123 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         }
     } else if (wid >= EPI_WARPS) {
         // ================================ producer ================================
+        // Warp pw owns edges 8 pw .. 8 pw + 7 of every tile; a lane owns 8 channels (128-bit loads / stores).
+        //   * pq is pre-scaled by 1/2 (api.cu), wr / wd are halved here: hv = Pa' + Pb' + r2 wr' + d0 wd' feeds
+        //     SiLU(2 hv) = hv + hv tanh(hv) directly (FADD, 2 FFMA, MUFU, FFMA per element).
+        //   * Pb rows stream through an 8-slot register pipeline (no L1 allocation): the slot of edge i is refilled
+        //     with edge i of the NEXT tile right after edge i is computed, so a gather has a whole tile to land.
+        //   * Pa changes once per CSR row run: a warp-uniform branch reloads it; the rows a tile will need are
+        //     pulled into L1 one tile ahead (one 32-sector touch per row), so the reload is an L1 hit.
+        //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
         const int pw = wid - EPI_WARPS;
         float wr[8], wd[8];
         unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
         unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wr[k] *= 0.5f; wd[k] *= 0.5f; }
+        const uint32_t ldp = (uint32_t)a.ldp;                                            // row index * ldp fits 32 bits (checked at launch)
         const float* pa_base = a.p + a.off_a + 8 * lane;
         const float* pb_base = a.p + a.off_b + 8 * lane;
+        const float* pa_touch = pa_base;                                                 // lane l touches sector l of a 1 KB row
+        const uint32_t x_lane = smem_u32(s.x[0]) + (uint32_t)(((lane >> 3) << 13) | (pw << 10) | ((lane & 7) << 4));
 
-        // metadata of the warp's 8 edges lives on lanes 0-7 and is software-pipelined one tile ahead:
-        //   (1) top of tile t: issue the (row, col, d0) loads of tile t+1
-        //   (2) after the first half of tile t: their results have landed -> issue the x loads of moved endpoints
-        //   (3) end of tile t: squared distance in the current frame (coord2diff, egnn_new.py:265-268)
-        int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f; bool m_valid = false;
-        auto load_rc = [&](int it, int& r, int& c, float& d0, bool& valid) {
+        // Edges past E (last tile only) are processed as edge (0, 0): finite garbage in columns nobody reads.
+        int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
+        auto load_rc = [&](int it, int& r, int& c, float& d0) {
             const int e = (blockIdx.x + it * gridDim.x) * TILE + 8 * pw + lane;
-            valid = (it < my_tiles) && lane < 8 && e < E;
             r = 0; c = 0; d0 = 0.f;
-            if (valid) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
+            if (it < my_tiles && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
         };
-        auto dist2 = [&](int r, int c) {
-            const float dx = a.x[3 * r] - a.x[3 * c], dy = a.x[3 * r + 1] - a.x[3 * c + 1], dz = a.x[3 * r + 2] - a.x[3 * c + 2];
-            return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        // L1 prefetch of the distinct rows of a group: one cp.async.ca per row, lane l pulling sector l of the
+        // 1 KB row through L1 into a scratch word — no destination register, so nothing ever waits on it
+        const uint32_t scratch = smem_u32(&s.touch[pw][lane]);
+        auto touch_rows = [&](int rows_on_lanes) {
+            const int prev = __shfl_up_sync(0xffffffffu, rows_on_lanes, 1);
+            unsigned fm = __ballot_sync(0xffffffffu, lane < 8 && (lane == 0 || rows_on_lanes != prev));
+            while (fm) {
+                const int i = __ffs(fm) - 1;
+                fm &= fm - 1;
+                const int r = __shfl_sync(0xffffffffu, rows_on_lanes, i);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(pa_touch + (uint32_t)r * ldp) : "memory");
+            }
         };
-        load_rc(0, m_row, m_col, m_d0, m_valid);
+        // metadata runs two tiles ahead: m_ = this tile (complete), n_ = next tile (r2 pending), f_ = loading
+        auto dist2 = [&](float xr0, float xr1, float xr2, float xc0, float xc1, float xc2) {
+            const float dx = xr0 - xc0, dy = xr1 - xc1, dz = xr2 - xc2;
+            return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
+        };
+        int n_row, n_col; float n_d0;
+        load_rc(0, m_row, m_col, m_d0);
+        load_rc(1, n_row, n_col, n_d0);
         m_r2 = m_d0;
-        if (m_valid && (m_row < a.n_moving || m_col < a.n_moving)) m_r2 = dist2(m_row, m_col);
+        if (m_row < a.n_moving || m_col < a.n_moving)                                    // an endpoint moved since the graph build
+            m_r2 = dist2(a.x[3 * m_row], a.x[3 * m_row + 1], a.x[3 * m_row + 2], a.x[3 * m_col], a.x[3 * m_col + 1], a.x[3 * m_col + 2]);
+        touch_rows(m_row);
+        float4 pb[8][2];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                                                    // fill the pipeline: the first tile
+            const int c = __shfl_sync(0xffffffffu, m_col, u);
+            const float* rb = pb_base + (uint32_t)c * ldp;
+            pb[u][0] = ldg_na(rb); pb[u][1] = ldg_na(rb + 4);
+        }
+        float cur[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = 0.f;
+        int cur_row = -1;
+        unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
+        const int l74 = (lane & 7) << 4;
 
         for (int it = 0; it < my_tiles; ++it) {
             const int xs = it % N_XS;
-            int n_row, n_col; float n_d0, n_r2; bool n_valid;
+            int f_row, f_col; float f_d0;
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 0);
-            load_rc(it + 1, n_row, n_col, n_d0, n_valid);                               // (1)
+            load_rc(it + 2, f_row, f_col, f_d0);
+            // next tile: coordinates of moved endpoints (unconditional loads of a valid address, no branch) and L1 touch of its Pa rows
+            const bool n_moving = n_row < a.n_moving || n_col < a.n_moving;
+            const int xr_i = n_moving ? 3 * n_row : 0, xc_i = n_moving ? 3 * n_col : 0;
+            const float xr0 = a.x[xr_i], xr1 = a.x[xr_i + 1], xr2 = a.x[xr_i + 2];
+            const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
+            touch_rows(n_row);
             mbar_wait(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
-            unsigned char* xt = s.x[xs];
-            float cur[8];                                                                // Pa chunk of the current row run
+            unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
+            // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cur[k] = 0.f;
-            int prev_row = -1;
-            float xr0 = 0.f, xr1 = 0.f, xr2 = 0.f, xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
-            bool n_moving = false;
+            for (int i = 0; i < 8; ++i) {
+                const int row = __shfl_sync(0xffffffffu, m_row, i);
+                const float r2 = __shfl_sync(0xffffffffu, m_r2, i);
+                const float d0 = __shfl_sync(0xffffffffu, m_d0, i);
+                ldg8_if(cur, pa_base + (uint32_t)row * ldp, row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
+                cur_row = row;
+                float vb[8], y[8];
+                unpack8(pb[i][0], pb[i][1], vb);
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                float4 pa[4][2], pb[4][2];
-                int rows[4]; bool fresh[4], ok[4]; float r2v[4], d0v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = 4 * hb + u;
-                    rows[u] = __shfl_sync(0xffffffffu, m_row, i);
-                    const int c = __shfl_sync(0xffffffffu, m_col, i);
-                    ok[u] = __shfl_sync(0xffffffffu, (int)m_valid, i) != 0;
-                    r2v[u] = __shfl_sync(0xffffffffu, m_r2, i);
-                    d0v[u] = __shfl_sync(0xffffffffu, m_d0, i);
-                    fresh[u] = ok[u] && rows[u] != prev_row;
-                    if (ok[u]) {
-                        const float* rb = pb_base + (size_t)c * a.ldp;
-                        pb[u][0] = *reinterpret_cast<const float4*>(rb); pb[u][1] = *reinterpret_cast<const float4*>(rb + 4);
-                        prev_row = rows[u];
-                    }
-                    if (fresh[u]) {
-                        const float* ra = pa_base + (size_t)rows[u] * a.ldp;
-                        pa[u][0] = *reinterpret_cast<const float4*>(ra); pa[u][1] = *reinterpret_cast<const float4*>(ra + 4);
-                    }
-                }
-                if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2 + 2 * hb);
-                if (hb == 1) {                                                          // (2)
-                    n_moving = n_valid && (n_row < a.n_moving || n_col < a.n_moving);
-                    if (n_moving) {
-                        xr0 = a.x[3 * n_row]; xr1 = a.x[3 * n_row + 1]; xr2 = a.x[3 * n_row + 2];
-                        xc0 = a.x[3 * n_col]; xc1 = a.x[3 * n_col + 1]; xc2 = a.x[3 * n_col + 2];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = 8 * pw + 4 * hb + u;                                   // edge index inside the tile
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if (fresh[u]) unpack8(pa[u][0], pa[u][1], cur);
-                    if (ok[u]) {
-                        float vb[8], y[8];
-                        unpack8(pb[u][0], pb[u][1], vb);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            y[k] = silu_tc<FMT>(fmaf(d0v[u], wd[k], fmaf(r2v[u], wr[k], cur[k] + vb[k])));
-                        o = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
-                    }
-                    *reinterpret_cast<uint4*>(xt + chunk_offset(i, lane, X_PANEL_BYTES)) = o;
-                }
-                if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 3 + 2 * hb);
+                for (int k = 0; k < 8; ++k)
+                    y[k] = silu_half<FMT>(fmaf(d0, wd[k], fmaf(r2, wr[k], cur[k] + vb[k])));
+                *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) =            // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
+                    make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+                // refill the slot with the same edge of the next tile
+                const int c = __shfl_sync(0xffffffffu, n_col, i);
+                const float* rb = pb_base + (uint32_t)c * ldp;
+                pb[i][0] = ldg_na(rb); pb[i][1] = ldg_na(rb + 4);
             }
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
             fence_proxy_async();                                                        // generic-proxy writes -> async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s.bar_full[xs]));
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 6);
-            n_r2 = n_d0;                                                                // (3)
-            if (n_moving) {
-                const float dx = xr0 - xc0, dy = xr1 - xc1, dz = xr2 - xc2;
-                n_r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            }
-            m_row = n_row; m_col = n_col; m_d0 = n_d0; m_r2 = n_r2; m_valid = n_valid;
+            m_row = n_row; m_col = n_col; m_d0 = n_d0;
+            m_r2 = n_moving ? dist2(xr0, xr1, xr2, xc0, xc1, xc2) : n_d0;
+            n_row = f_row; n_col = f_col; n_d0 = f_d0;
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ epilogue ================================
         static_assert(REGS_EPILOGUE == 96, "the epilogue keeps its launch allocation");
         const int ew = wid, q = ew & 3, gi = ew >> 2;
         const int c0 = 32 * q + lane, c1 = c0 + 128;                                     // this thread's two channels
-        const float b2_0 = a.b2[c0], b2_1 = a.b2[c1];
+        const float hb0 = 0.5f * a.b2[c0], hb1 = 0.5f * a.b2[c1];         // SiLU(v + b) from hv = v / 2 + b / 2
         const bool gated = a.coord || a.attention;
         const float wv0 = gated ? a.wv[c0] : 0.f, wv1 = gated ? a.wv[c1] : 0.f;
         static_assert(H == 256, "segment stores shift by 8");
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v0[j] = silu_tc<FMT>(v0[j] + b2_0); v1[j] = silu_tc<FMT>(v1[j] + b2_1); }
+            for (int j = 0; j < 32; ++j) { v0[j] = silu_half<FMT>(fmaf(0.5f, v0[j], hb0)); v1[j] = silu_half<FMT>(fmaf(0.5f, v1[j], hb1)); }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 3);
             float gate = 1.f;
             if (gated) {
@@ -410,6 +422,8 @@ int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
              "tc edge layer %d has no weight image", lin_id);
     const TcLinearImg& L = h->tc->lin[lin_id];
     DP_CHECK(L.K == H && L.n_out == H, DP_ERR_INVALID, "tc edge layer %d: shape mismatch", lin_id);
+    DP_CHECK((unsigned long long)h->plan.N * (unsigned long long)a.ldp < (1ull << 32), DP_ERR_INVALID,
+             "batch of %d nodes exceeds the 32-bit element indexing of the projected features", h->plan.N);
     const int smem = (int)sizeof(EdgeSmem) + 1024;
     const int grid = h->sm_count;
     const unsigned char* img = L.img[fmt];

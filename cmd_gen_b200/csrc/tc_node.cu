@@ -50,7 +50,7 @@ struct NodeArgs {
     int n_rows;
     int do_mlp;                                  // 0: projection only (h version 0, straight from the embedding)
     const float* b3; const float* b4;            // node_mlp biases
-    const float* bp;                             // projection bias [n_blocks * 256]
+    const float* bp;                             // projection bias [n_blocks * 256], pre-scaled by 1/2 like the weight image
     float* pq; int ldp; int n_blocks;            // projection output [N][ldp], n_blocks x 256 channels
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
 };
@@ -380,7 +380,7 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     NodeArgs a{};
     a.h = p.h; a.aggv = av; a.n_rows = p.N; a.do_mlp = v > 0;
     if (v > 0) { a.b3 = W.gcl[v - 1].n0.b; a.b4 = W.gcl[v - 1].n2.b; }
-    a.bp = ps.lin.b; a.pq = p.pq; a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
+    a.bp = ps.b_half; a.pq = p.pq; a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
     a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;
