@@ -32,13 +32,29 @@ __device__ __forceinline__ void warp_linear(const float (&in)[4], int K, const f
 {
 #pragma unroll
     for (int m = 0; m < MAX_OUT32; ++m) out[m] = (lane + 32 * m < n_out) ? b[lane + 32 * m] : 0.f;
-    for (int k = 0; k < K; ++k) {
-        const int src = k & 31, reg = k >> 5;
-        const float v = __shfl_sync(0xffffffffu, reg == 0 ? in[0] : reg == 1 ? in[1] : reg == 2 ? in[2] : in[3], src);
-        const float* wr = w + (size_t)k * n_out;
+    // weights of KC consecutive inputs are fetched together (independent loads: one L2 round trip per chunk,
+    // not per input); the FMA chain itself stays in ascending k
+    constexpr int KC = MAX_OUT32 >= 8 ? 4 : 8;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        float wv[KC][MAX_OUT32];
 #pragma unroll
-        for (int m = 0; m < MAX_OUT32; ++m)
-            if (lane + 32 * m < n_out) out[m] = fmaf(v, wr[lane + 32 * m], out[m]);
+        for (int kk = 0; kk < KC; ++kk) {
+            const float* wr = w + (size_t)(k0 + kk) * n_out;
+#pragma unroll
+            for (int m = 0; m < MAX_OUT32; ++m)
+                wv[kk][m] = (k0 + kk < K && lane + 32 * m < n_out) ? wr[lane + 32 * m] : 0.f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int k = k0 + kk;
+            const int src = k & 31, reg = k >> 5;
+            const float v = __shfl_sync(0xffffffffu, reg == 0 ? in[0] : reg == 1 ? in[1] : reg == 2 ? in[2] : in[3], src);
+            if (k < K) {
+#pragma unroll
+                for (int m = 0; m < MAX_OUT32; ++m)
+                    if (lane + 32 * m < n_out) out[m] = fmaf(v, wv[kk][m], out[m]);
+            }
+        }
     }
 }
 

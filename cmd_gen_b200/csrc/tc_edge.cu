@@ -279,15 +279,21 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             // image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 128 packed 32-bit columns.
             const int r = 128 * gi + 32 * q + lane;
 #pragma unroll 1
-            for (int kp = 0; kp < 4; ++kp) {
+            for (int kp = 0; kp < 4; kp += 2) {                                          // two panels (16 loads per thread) in flight
                 const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
-                uint32_t wreg[32];
+                uint32_t wa[32], wb[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
-                    wreg[4 * c] = t.x; wreg[4 * c + 1] = t.y; wreg[4 * c + 2] = t.z; wreg[4 * c + 3] = t.w;
+                    wa[4 * c] = t.x; wa[4 * c + 1] = t.y; wa[4 * c + 2] = t.z; wa[4 * c + 3] = t.w;
                 }
-                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32, wreg);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 t = *reinterpret_cast<const uint4*>(src + W_PANEL_BYTES + ((c ^ (r & 7)) << 4));
+                    wb[4 * c] = t.x; wb[4 * c + 1] = t.y; wb[4 * c + 2] = t.z; wb[4 * c + 3] = t.w;
+                }
+                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32, wa);
+                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32 + 32, wb);
             }
             tmem_st_wait();
             tc_fence_before();
