@@ -112,6 +112,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
         h->tc_mask = atoi(m) ? 3 : 0;
     }
     if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
+    if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
             h->trace_kernel = atoi(m);
@@ -343,6 +344,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
         const double nb = (double)phar_counts[b] + res_counts[b];
         pairs += nb * nb;
         if (phar_counts[b] > p.max_phar) p.max_phar = phar_counts[b];
+        if (phar_counts[b] + res_counts[b] > p.max_nodes) p.max_nodes = phar_counts[b] + res_counts[b];
     }
     p.B = B; p.Np = poff[B]; p.Nr = roff[B]; p.N = p.Np + p.Nr;
     DP_CHECK(p.N > 0, DP_ERR_INVALID, "dp_plan: empty batch");
@@ -368,6 +370,10 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1);
     ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.edst, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
     ALLOC(p.counts, 4);
+    // bucketed cell list: pays off once a sample has more nodes than a handful of warp sweeps (full-atom pockets)
+    p.use_cells = c.edge_cutoff > 0.f && p.max_nodes <= CELL_SAMPLE_MAX_NODES &&
+                  (h->graph_mode == 2 || (h->graph_mode == 0 && p.max_nodes >= 512));
+    if (p.use_cells) { ALLOC(p.cell_start, (size_t)B * (CELLS_MAX + 1)); ALLOC(p.cell_nodes, p.N); ALLOC(p.cell_grid, (size_t)B * 8); }
     ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.h_base, (size_t)p.Nr * H);
     ALLOC(p.agg, ((size_t)p.N + units * 2) * H);          // [agg rows | partial rows] contiguous (graph.cu edge_dst)
     p.partials = p.agg + (size_t)p.N * H;

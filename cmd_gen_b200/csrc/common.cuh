@@ -9,6 +9,9 @@
 constexpr int H = 256;            // hidden_nf (compile-time tile width)
 constexpr int UNIT_F32 = 64;      // edges per segmented-sum unit, FFMA path
 constexpr int UNIT_TC = 32;       // edges per segmented-sum unit, tcgen05 path
+constexpr int CELLS_DIM_MAX = 16;                 // cells per axis of one sample's grid
+constexpr int CELLS_MAX = CELLS_DIM_MAX * CELLS_DIM_MAX * CELLS_DIM_MAX;
+constexpr int CELL_SAMPLE_MAX_NODES = 8192;       // per-row bitmap of the cell-list builder: 256 words per warp
 constexpr int DP_TRACE_WORDS = 4 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
 
 void dp_set_error(const char* fmt, ...);
@@ -150,6 +153,7 @@ struct Plan {
     int B = 0, Np = 0, Nr = 0, N = 0;
     int64_t Ecap = 0;
     int max_phar = 0;
+    int max_nodes = 0;           // largest sample (phar + pocket nodes)
     // layout
     int* phar_off = nullptr;     // [B+1]
     int* res_off = nullptr;      // [B+1]
@@ -162,6 +166,11 @@ struct Plan {
     int* edst = nullptr;         // [Ecap] segmented-sum destination per edge for 32-edge units (see graph.cu)
     float* d0 = nullptr;         // [Ecap] squared input-frame distances (edge_attr, egnn_new.py:195)
     int* counts = nullptr;       // [4]: E, E_p, overflow, spare
+    // cell list of the bucketed radius-graph builder (graph.cu), rebuilt by every denoiser evaluation
+    int use_cells = 0;
+    int* cell_start = nullptr;   // [B][CELLS_MAX + 1] offsets into cell_nodes (absolute)
+    int* cell_nodes = nullptr;   // [N] node ids bucketed by cell, samples back to back
+    float* cell_grid = nullptr;  // [B][8]: origin xyz, inverse cell size xyz, dims packed (nx | ny << 8 | nz << 16) as int bits
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
@@ -200,6 +209,7 @@ struct dp_handle {
     int sm_count = 148;
     int precision = 0;
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
+    int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells
     int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
     DeviceWeights w;

@@ -1,9 +1,13 @@
 // K1 — radius graph as CSR.  Replaces EGNNDynamics.get_edges
 // (DiffPhar/equivariant_diffusion/dynamics.py:141-147): the reference materialises a dense
-// N x N adjacency (cdist + mask compare + nonzero).  Here each row scans only the nodes of
-// its own sample (the only possible neighbours), one warp per row, candidates visited in
-// ascending node index so ballot compaction emits columns already sorted — the (row, col)
-// lexicographic order torch.where yields.  Integer outputs are bit-exact by construction.
+// N x N adjacency (cdist + mask compare + nonzero).  Two builders, identical output:
+//   * scan  (small samples, C-alpha pockets): one warp per row sweeps the nodes of the row's own sample
+//     (the only possible neighbours) in ascending node index; ballot compaction emits sorted columns.
+//   * cells (samples of >= 512 nodes, full-atom pockets): a bucketed cell list per sample (cells >= cutoff,
+//     <= 16 per axis, rebuilt per call because the phar nodes move and the pocket is re-centred), one warp
+//     per row tests the 27 neighbouring buckets and records hits in a per-warp BITMAP over the sample's
+//     nodes; reading the bitmap in word order emits the columns sorted, whatever order the buckets hold.
+// Either way the output is the (row, col) lexicographic order torch.where yields, bit-exact by construction.
 //
 // Predicate (contract, SURVEY.md §7 hard part 1):
 //   fp32  sqrt((dx*dx + dy*dy) + dz*dz) <= cutoff, every op rounded separately (no FMA).
@@ -24,6 +28,7 @@ struct GraphArgs {
     int* col; int* erow; float* d0; int* edst;
     int* counts;           // [0]=E [1]=E_p [2]=overflow
     long long ecap;
+    int* cell_start; int* cell_nodes; float* cell_grid;
 };
 
 __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float xj, float yj, float zj)
@@ -89,6 +94,178 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
     }
 }
 
+// ---- bucketed cell list --------------------------------------------------------------------------
+__device__ __forceinline__ int cell_coord(float x, float origin, float inv, int n)
+{
+    const int c = (int)floorf(__fmul_rn(__fsub_rn(x, origin), inv));   // monotone in x: neighbours within the cutoff differ by <= 1
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+// One CTA per sample: bounding box -> grid (cell >= 1.001 cutoff per axis, <= 16 cells per axis) -> histogram ->
+// exclusive scan -> bucket fill.  Bucket order is arbitrary (atomics); the row kernel's bitmap restores order.
+__global__ void __launch_bounds__(256) cell_build_kernel(GraphArgs a)
+{
+    __shared__ float red[6][8];
+    __shared__ float grid[8];
+    __shared__ int hist[CELLS_MAX + 1];
+    __shared__ int wsum[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int p0 = a.phar_off[b], np = a.phar_off[b + 1] - p0;
+    const int r0 = a.Np + a.res_off[b], nr = a.res_off[b + 1] - a.res_off[b];
+    const int n = np + nr;
+    auto node_of = [&](int i) { return i < np ? p0 + i : r0 + (i - np); };
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = tid; i < n; i += 256) {
+        const int j = node_of(i);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float v = a.x[3 * j + d]; mn[d] = fminf(mn[d], v); mx[d] = fmaxf(mx[d], v); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+        if (lane == 0) { red[d][wid] = mn[d]; red[3 + d][wid] = mx[d]; }
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float lo = red[tid][0], hi = red[3 + tid][0];
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, red[tid][w]); hi = fmaxf(hi, red[3 + tid][w]); }
+        if (n == 0) { lo = 0.f; hi = 0.f; }
+        const float ext = hi - lo;
+        float cs = 1.001f * a.cutoff;
+        int nc = (int)(ext / cs) + 1;
+        if (nc > CELLS_DIM_MAX) { nc = CELLS_DIM_MAX; cs = 1.001f * ext / CELLS_DIM_MAX; }
+        grid[tid] = lo; grid[3 + tid] = 1.0f / cs;
+        red[tid][0] = __int_as_float(nc);
+    }
+    __syncthreads();
+    const int nx = __float_as_int(red[0][0]), ny = __float_as_int(red[1][0]), nz = __float_as_int(red[2][0]);
+    const int n_cells = nx * ny * nz;
+    if (tid == 0) grid[6] = __int_as_float(nx | (ny << 8) | (nz << 16));
+    for (int c = tid; c <= n_cells; c += 256) hist[c] = 0;
+    __syncthreads();
+    if (tid < 7) a.cell_grid[8 * b + tid] = grid[tid];
+    auto cell_of = [&](int j) {
+        const int cx = cell_coord(a.x[3 * j], grid[0], grid[3], nx);
+        const int cy = cell_coord(a.x[3 * j + 1], grid[1], grid[4], ny);
+        const int cz = cell_coord(a.x[3 * j + 2], grid[2], grid[5], nz);
+        return (cz * ny + cy) * nx + cx;
+    };
+    for (int i = tid; i < n; i += 256) atomicAdd(&hist[cell_of(node_of(i))], 1);
+    __syncthreads();
+    // exclusive scan of hist[0 .. n_cells) in chunks of 256
+    int carry = 0;
+    for (int c0 = 0; c0 < n_cells; c0 += 256) {
+        const int c = c0 + tid;
+        const int v = c < n_cells ? hist[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < wid; ++w) before += wsum[w];
+        int total = 0;
+        for (int w = 0; w < 8; ++w) total += wsum[w];
+        if (c < n_cells) hist[c] = carry + before + incl - v;
+        carry += total;
+        __syncthreads();
+    }
+    const int base = p0 + a.res_off[b];                    // nodes of earlier samples
+    int* cs_out = a.cell_start + (size_t)b * (CELLS_MAX + 1);
+    for (int c = tid; c < n_cells; c += 256) cs_out[c] = base + hist[c];
+    if (tid == 0) cs_out[n_cells] = base + n;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int j = node_of(i);
+        const int pos = atomicAdd(&hist[cell_of(j)], 1);
+        a.cell_nodes[base + pos] = j;
+    }
+}
+
+// One warp per row: hits of the 27 neighbouring buckets go into the warp's bitmap over the sample's nodes
+// (local index = position in ascending node order: the sample's phar nodes, then its pocket nodes).
+template <bool FILL>
+__global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
+{
+    __shared__ unsigned bitmap_s[8][CELL_SAMPLE_MAX_NODES / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned* bm = bitmap_s[wid];
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int row = blockIdx.x * 8 + wid; row < a.N; row += gridDim.x * 8) {
+        const int b = a.sample_of[row];
+        const int p0 = a.phar_off[b], np = a.phar_off[b + 1] - p0;
+        const int r0 = a.Np + a.res_off[b], nr = a.res_off[b + 1] - a.res_off[b];
+        const int n_words = (np + nr + 31) >> 5;
+        for (int w = lane; w < n_words; w += 32) bm[w] = 0u;
+        __syncwarp();
+        const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
+        const float* g = a.cell_grid + 8 * b;
+        const int dims = __float_as_int(g[6]);
+        const int nx = dims & 255, ny = (dims >> 8) & 255, nz = dims >> 16;
+        const int cx = cell_coord(xi, g[0], g[3], nx), cy = cell_coord(yi, g[1], g[4], ny), cz = cell_coord(zi, g[2], g[5], nz);
+        const int* cs = a.cell_start + (size_t)b * (CELLS_MAX + 1);
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= nz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= ny) continue;
+                // the x-neighbours are consecutive buckets: one contiguous candidate range per (y, z)
+                const int c_lo = (z * ny + y) * nx + (cx > 0 ? cx - 1 : 0);
+                const int c_hi = (z * ny + y) * nx + (cx + 1 < nx ? cx + 1 : nx - 1);
+                const int k_end = cs[c_hi + 1];
+                for (int k = cs[c_lo] + lane; k < k_end; k += 32) {
+                    const int j = a.cell_nodes[k];
+                    const float d2 = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                    if (__fsqrt_rn(d2) <= a.cutoff) {
+                        const int loc = j < a.Np ? j - p0 : np + (j - r0);
+                        atomicOr(&bm[loc >> 5], 1u << (loc & 31));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        long long base = FILL ? (long long)a.rowptr[row] : 0;
+        const long long row_start = base;
+        const long long row_end = FILL ? (long long)a.rowptr[row + 1] : 0;
+        int found = 0;
+        for (int w0 = 0; w0 < n_words; w0 += 32) {
+            const int w = w0 + lane;
+            unsigned bits = w < n_words ? bm[w] : 0u;
+            const int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (FILL) {
+                long long pos = base + found + incl - cnt;
+                while (bits) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int loc = (w << 5) + bit;
+                    const int j = loc < np ? p0 + loc : r0 + (loc - np);
+                    if (pos < a.ecap) {
+                        a.col[pos] = j;
+                        a.erow[pos] = row;
+                        a.d0[pos] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                        a.edst[pos] = edge_dst(a.N, row, row_start, row_end, pos);
+                    }
+                    ++pos;
+                }
+            }
+            found += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (!FILL && lane == 0) a.deg[row] = found;
+        __syncwarp();
+    }
+}
+
 // Exclusive scan of deg[N] -> rowptr[N+1] by one CTA (N <= a few million: microseconds).
 __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict__ deg, int* __restrict__ rowptr,
                                                           int N, int Np, int* counts, long long ecap)
@@ -148,15 +325,24 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     a.N = p.N; a.Np = p.Np; a.cutoff = h->cfg.edge_cutoff;
     a.deg = p.deg; a.rowptr = p.rowptr; a.col = p.col; a.erow = p.erow; a.d0 = p.d0; a.edst = p.edst;
     a.counts = p.counts; a.ecap = p.Ecap;
+    a.cell_start = p.cell_start; a.cell_nodes = p.cell_nodes; a.cell_grid = p.cell_grid;
     const int wpb = 8;
     int grid = (p.N + wpb - 1) / wpb;
     const int max_grid = h->sm_count * 16;
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     prof_begin(h, PROF_GRAPH, st);
-    DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));
-    DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
-    DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<true>, dim3(grid), dim3(256), 0, st, a));
+    if (p.use_cells) {
+        DP_CUDA(launch_kernel(h->pdl, cell_build_kernel, dim3(p.B), dim3(256), 0, st, a));
+        DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<false>, dim3(grid), dim3(256), 0, st, a));
+        DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
+        DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<true>, dim3(grid), dim3(256), 0, st, a));
+        h->launches += 1;
+    } else {
+        DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));
+        DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
+        DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<true>, dim3(grid), dim3(256), 0, st, a));
+    }
     prof_end(h, st);
     h->launches += 3;
     DP_CUDA(cudaGetLastError());

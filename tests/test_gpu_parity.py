@@ -27,8 +27,18 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32"):
-    h = _lib.Handle(cfg, DEV, precision)
+def make_handle(cfg, wseed, precision="fp32", graph=None):
+    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH)."""
+    import os
+    old = os.environ.pop("DIFFPHAR_GRAPH", None)
+    if graph:
+        os.environ["DIFFPHAR_GRAPH"] = graph
+    try:
+        h = _lib.Handle(cfg, DEV, precision)
+    finally:
+        os.environ.pop("DIFFPHAR_GRAPH", None)
+        if old is not None:
+            os.environ["DIFFPHAR_GRAPH"] = old
     h.set_weights(pack_blob(cfg, init_weights(cfg, wseed)))
     return h
 
@@ -41,11 +51,12 @@ def csr_to_coo(rowptr, col):
 
 
 # ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("graph", ["scan", "cells"])
 @pytest.mark.parametrize("name", CASES)
-def test_edges_bit_exact_vs_reference(name):
+def test_edges_bit_exact_vs_reference(name, graph):
     g = load(f"dynamics_{name}.npz")
     cfg = case_config(name)
-    h = make_handle(cfg, int(g["wseed"]))
+    h = make_handle(cfg, int(g["wseed"]), graph=graph)
     h.plan(g["counts"], g["sizes"])
     x = torch.cat([T(g["z"])[:, :3], T(g["xh_pocket"])[:, :3]]).to(DEV)
     rowptr, col = h.build_edges(x)
@@ -54,10 +65,11 @@ def test_edges_bit_exact_vs_reference(name):
     assert np.array_equal((rowptr[1:] - rowptr[:-1]).cpu().numpy(), ref_deg)
 
 
-@pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.05, 700, 12, 6)])
-def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B):
+@pytest.mark.parametrize("graph", ["scan", "cells"])
+@pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.05, 700, 12, 6), (0.05, 2000, 12, 3)])
+def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B, graph):
     cfg = DynamicsConfig(residue_nf=20)
-    h = make_handle(DynamicsConfig(n_layers=1), 0)
+    h = make_handle(DynamicsConfig(n_layers=1), 0, graph=graph)
     pocket = make_pocket_batch([n_res], 20, density=density, seed=5, replicate=B)
     gen = torch.Generator().manual_seed(9)
     com = pocket["x"][:n_res].mean(0)
@@ -75,6 +87,39 @@ def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B):
     fl = h.flags()
     assert fl.last_n_edges == ref.shape[1] and fl.edge_overflow == 0
     assert fl.last_n_edges_phar == int((ref[0] < B * n_phar).sum())
+
+
+@pytest.mark.parametrize("n_res,n_phar,B,density", [(2000, 10, 16, 0.05), (4000, 12, 4, 0.05), (300, 4, 40, 0.0074)])
+def test_edges_cells_equal_scan_at_config_sizes(n_res, n_phar, B, density):
+    """config 3 (full-atom, ~2k pocket nodes, B=16) and config 5 (4k-node pockets, 12 phar points) sizes: the bucketed
+    cell list and the per-sample scan must emit the same CSR, bit for bit; ragged sizes, distinct pockets, phar
+    points far outside the pocket (own buckets), coincident points and an empty sample included."""
+    sizes = [n_res - 37 * (i % 5) for i in range(B)]
+    counts = [max(0, n_phar - (i % 3)) for i in range(B)]
+    sizes[1], counts[1] = 0, 0                                        # an empty sample
+    pocket = make_pocket_batch(sizes, 20, density=density, seed=11)
+    gen = torch.Generator().manual_seed(12)
+    xp = 30.0 * torch.randn(sum(counts), 3, generator=gen)            # some phar points far from any residue
+    if xp.shape[0] > 3:
+        xp[1] = xp[0]                                                 # coincident points
+        xp[2] = pocket["x"][5]                                        # a phar point on top of a residue of its own sample
+    x = torch.cat([xp, pocket["x"]]).to(DEV)
+    out = {}
+    for graph in ("scan", "cells"):
+        h = make_handle(DynamicsConfig(n_layers=1), 0, graph=graph)
+        h.plan(counts, sizes)
+        rowptr, col = h.build_edges(x)
+        fl = h.flags()
+        assert fl.edge_overflow == 0
+        out[graph] = (rowptr.cpu().clone(), col.cpu()[: fl.last_n_edges].clone(), fl.last_n_edges_phar)
+    assert torch.equal(out["scan"][0], out["cells"][0])
+    assert torch.equal(out["scan"][1], out["cells"][1])
+    assert out["scan"][2] == out["cells"][2]
+    rowptr, col, _ = out["cells"]
+    deg = (rowptr[1:] - rowptr[:-1])
+    assert int(deg.min()) >= 1                                        # every node has its self loop
+    row = torch.repeat_interleave(torch.arange(deg.numel()), deg)
+    assert bool(((col[1:] > col[:-1]) | (row[1:] != row[:-1])).all())  # columns ascending inside a row
 
 
 def test_edge_capacity_overflow_is_reported():
@@ -155,6 +200,45 @@ def test_tensor_core_modes_at_full_size_agree_with_fp32():
         assert (a[:, 3:] - ref_p[:, 3:]).abs().max() <= tol_h * max(1.0, float(ref_p[:, 3:].abs().max()))
         assert (r[:, 3:] - ref_r[:, 3:]).abs().max() <= tol_h * max(1.0, float(ref_r[:, 3:].abs().max()))
         assert (a[:, :3] - ref_p[:, :3]).abs().max() <= 1e-5 * 60 + tol_v * float(ref_p[:, :3].abs().max())
+
+
+@pytest.mark.parametrize("label,n_res,n_ph,B,res_nf,n_layers,density", [
+    ("config3 full-atom ~2k pocket nodes, B=16", 2000, 8, 16, 11, 5, 0.05),
+    ("config5 4k-node pockets, 12 phar points, 9 blocks", 4000, 12, 2, 11, 9, 0.05)])
+def test_large_pocket_configs_tensor_core_vs_fp32(label, n_res, n_ph, B, res_nf, n_layers, density):
+    """BASELINE configs 3 and 5 at full size (E ~ 1.3 M / 0.7 M edges, cell-list graph builder, rows spanning many
+    32-edge units): the 16-bit tensor-core modes against the fp32 FFMA mode of the same library, the f16
+    ("TF32-class", 10-bit mantissa) error below the bf16 error, CSR identical across modes."""
+    cfg = DynamicsConfig(residue_nf=res_nf, n_layers=n_layers)
+    pocket = make_pocket_batch([n_res], res_nf, density=density, seed=21, replicate=B)
+    gen = torch.Generator().manual_seed(22)
+    com = pocket["x"][:n_res].mean(0)
+    z = torch.cat([com + 6.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(B * n_ph, 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    t = torch.full((B,), 0.3)
+    outs, edges = {}, {}
+    for prec in ("fp32", "f16", "bf16"):
+        h = make_handle(cfg, 0, prec)
+        h.plan([n_ph] * B, [n_res] * B)
+        a, r = h.dynamics_forward(z, xr, t)
+        fl = h.flags()
+        assert fl.edge_overflow == 0 and fl.nan_resets == 0
+        outs[prec] = (a.cpu(), r.cpu())
+        edges[prec] = (fl.last_n_edges, fl.last_n_edges_phar)
+    assert edges["fp32"] == edges["f16"] == edges["bf16"] and edges["fp32"][0] > 40 * B * n_res * 0.5
+    ref_p, ref_r = outs["fp32"]
+    errs = {}
+    for prec in ("f16", "bf16"):
+        tol_h, tol_v = TC_TOL[prec]
+        a, r = outs[prec]
+        eh = float(max((a[:, 3:] - ref_p[:, 3:]).abs().max(), (r[:, 3:] - ref_r[:, 3:]).abs().max()))
+        scale = max(1.0, float(ref_p[:, 3:].abs().max()), float(ref_r[:, 3:].abs().max()))
+        errs[prec] = eh / scale
+        # deeper / denser graphs than the goldens: rounding accumulates over 9 blocks and ~40 messages per node
+        assert eh <= 4 * tol_h * scale, (label, prec, eh, scale)
+        assert (a[:, :3] - ref_p[:, :3]).abs().max() <= 1e-5 * 80 + 2 * tol_v * float(ref_p[:, :3].abs().max())
+        assert torch.all(r[:, :3] == 0)
+    assert errs["f16"] < errs["bf16"], errs
 
 
 def test_dynamics_module_api_and_kwargs():
