@@ -8,11 +8,11 @@
 
 constexpr int H = 256;            // hidden_nf (compile-time tile width)
 constexpr int UNIT_F32 = 64;      // edges per segmented-sum unit, FFMA path
-constexpr int UNIT_TC = 32;       // edges per segmented-sum unit, tcgen05 path
+constexpr int UNIT_TC = 16;       // edges per segmented-sum unit, tcgen05 path (one epilogue group's share of a 64-edge tile)
 constexpr int CELLS_DIM_MAX = 16;                 // cells per axis of one sample's grid
 constexpr int CELLS_MAX = CELLS_DIM_MAX * CELLS_DIM_MAX * CELLS_DIM_MAX;
 constexpr int CELL_SAMPLE_MAX_NODES = 8192;       // per-row bitmap of the cell-list builder: 256 words per warp
-constexpr int DP_TRACE_WORDS = 4 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
+constexpr int DP_TRACE_WORDS = 6 * 64 * 16;   // debug timeline: [role][tile iteration][slot]
 
 void dp_set_error(const char* fmt, ...);
 
@@ -177,7 +177,7 @@ struct Plan {
     float* tbuf = nullptr;       // [N][H] node-MLP hidden
     float* agg = nullptr;        // [N][H]
     float* partials = nullptr;   // [units][2][H]
-    float* pq = nullptr;         // [N][1024]
+    float* pq = nullptr;         // [N][1024] fp32 (FFMA mode) or [N][1024] f16 pre-scaled by 1/2 (tcgen05 modes)
     float* x_in = nullptr;       // [N][3]
     float* x_a = nullptr;        // [N][3]
     float* x_b = nullptr;        // [N][3]

@@ -173,6 +173,21 @@ __device__ __forceinline__ float4 ldg_na(const float* p)
     asm("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// 16 bytes (8 halves) reloaded only when `take` is set: a predicated load straight into the live registers
+__device__ __forceinline__ void ldg4_if(uint4& v, const void* p, bool take)
+{
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %5, 0;\n"
+        "@q ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+        "}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((int)take));
+}
+__device__ __forceinline__ uint4 ldg_na_u4(const void* p)
+{
+    uint4 v;
+    asm("ld.global.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 // 32 bytes (8 floats) reloaded only when `take` is set: predicated loads straight into the live registers,
 // no branch (keeps the caller's loop one basic block, so independent edges interleave)
 __device__ __forceinline__ void ldg8_if(float (&v)[8], const float* p, bool take)

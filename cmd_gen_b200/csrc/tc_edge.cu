@@ -13,17 +13,18 @@
 // edges along TMEM columns, so the CSR segmented sum is a run of register FMAs inside one thread —
 // no atomics, no shuffles — and agg stores are 128 B coalesced.
 //
-// Warp-specialised, persistent (one CTA per SM, tiles round-robin):
-//   warps 0-7   epilogue : two independent groups of 4 warps; group g owns the g-th 32-edge unit of every tile.
-//                          Warp (g, q) reads TMEM lanes 32 q .. +32 of BOTH accumulator halves, so a thread
-//                          holds channels c and c + 128 for 32 edges: SiLU, gate (in-thread pre-add of the two
-//                          channels, one smem-transposed reduce per warp, 4-warp named barrier per group),
-//                          segmented sum as two independent FMA chains, stores.
-//   warps 8-15  producer : each warp owns 8 edges of the tile: gathers the pre-projected rows (Pa once per
-//                          CSR row run, Pb per edge; 128-bit loads, 8 in flight per lane), first layer,
-//                          writes the swizzled K-major B tile, fence.proxy.async, arrives on full[stage].
-//   warp  16    MMA      : (warps 17-19 idle: they only donate their registers, setmaxnreg) one thread waits full[stage] / tmem_empty[acc], issues 32 tcgen05.mma
-//                          (M=128, N=64, K=16) per tile and commits to x_empty[stage] + tmem_full[acc].
+// Warp-specialised, persistent (one CTA per SM, tiles round-robin), 28 warps = 7 per SM sub-partition:
+//   warps 0-15  epilogue : four independent groups of 4 warps; group g owns edges 16 g .. 16 g + 15 of every tile
+//                          (= one segmented-sum unit, UNIT_TC).  Warp (g, q) reads TMEM lanes 32 q .. +32 of BOTH
+//                          accumulator halves, so a thread holds channels c and c + 128 for 16 edges: SiLU, gate
+//                          (in-thread pre-add of the two channels, one smem-transposed reduce per warp, 4-warp named
+//                          barrier per group), segmented sum as two independent FMA chains, stores.
+//   warps 16-23 producer : each warp owns 8 edges of the tile: gathers the pre-projected f16 rows (Pa once per
+//                          CSR row run, Pb per edge, one 128-bit load per lane and row) through an 8-slot register
+//                          pipeline, first layer, swizzled K-major B tile, fence.proxy.async, arrive on full[stage].
+//   warp  24    MMA      : (warps 25-27 only donate registers, setmaxnreg) waits full[stage] / tmem_empty[acc]; one
+//                          elected lane issues 32 tcgen05.mma (M=128, N=64, K=16) per tile and commits to
+//                          x_empty[stage] + tmem_full[acc].
 // Second-layer weights are the A operand and stay resident in TENSOR MEMORY for the whole kernel (256
 // columns: 2 M-halves x 128 columns of packed 16-bit pairs, written once per CTA by the epilogue warps with
 // tcgen05.st), so an MMA reads only its 2 KB B tile from shared memory (the SS form read 6 KB: the
@@ -41,19 +42,23 @@ constexpr int N_TS = 2;                           // accumulator stages
 constexpr int TS_COLS = 2 * TILE;                 // TMEM columns per accumulator stage
 constexpr int W_COLS = 256;                       // TMEM columns of the resident weights: half hh at hh * 128, K pair j at column j
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_WARPS = 8, PRO_WARPS = 8;
+constexpr int EPI_WARPS = 16, PRO_WARPS = 8, EPI_GROUPS = EPI_WARPS / 4;
+constexpr int GROUP_EDGES = TILE / EPI_GROUPS;    // 16 = UNIT_TC
+static_assert(GROUP_EDGES == UNIT_TC, "an epilogue group owns exactly one segmented-sum unit");
 constexpr int MMA_WARP = EPI_WARPS + PRO_WARPS;
-constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 5 warpgroups: 2 epilogue, 2 producer, 1 MMA (+3 idle warps)
-// Registers are allocated per SM sub-partition (16384 each, 5 warps per sub-partition here), so the launch
-// gets 96 per thread; setmaxnreg then moves the idle warpgroup's share to the producers.
-constexpr int REGS_MMA = 32, REGS_PRODUCER = 120, REGS_EPILOGUE = 96;    // 2 Re + 2 Rp + Rm <= 5 x 96: the CTA pool only holds what its own warps released
+constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 epilogue, 2 producer, 1 MMA (+3 idle warps)
+// Registers are allocated per SM sub-partition (16384 each, 7 warps per sub-partition here), so the launch
+// gets 72 per thread; setmaxnreg then rebalances.  4 Re + 2 Rp + Rm <= 7 x 72: the CTA pool only holds what
+// its own warps released.
+constexpr int REGS_MMA = 32, REGS_PRODUCER = 104, REGS_EPILOGUE = 64;
+static_assert(4 * REGS_EPILOGUE + 2 * REGS_PRODUCER + REGS_MMA <= 7 * 72, "register pool");
 constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer (16 edges + pad)
 
 struct EdgeSmem {                                 // offsets from a 1024-aligned base
     unsigned char x[N_XS][X_TILE_BYTES];          // 128 KB
-    float red[EPI_WARPS][32 * RED_STRIDE];        // 20 KB: per-warp [channel pair][16 edges (+4 pad)]
-    float part[2][EPI_WARPS][32];                 // per-warp partial gate sums, double-buffered over tiles
-    float gate[EPI_WARPS][32];
+    float red[EPI_WARPS][32 * RED_STRIDE];        // 40 KB: per-warp [channel pair][16 edges (+4 pad)]
+    float part[2][EPI_WARPS][GROUP_EDGES];        // per-warp partial gate sums, double-buffered over tiles
+    float gate[EPI_WARPS][GROUP_EDGES];
     float touch[PRO_WARPS][32];                   // cp.async landing pad of the L1 row prefetch (never read)
     unsigned long long bar_w;
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 
     // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
     if (tid == 0) {
-        mbar_init(smem_u32(&s.bar_w), EPI_WARPS);
+        mbar_init(smem_u32(&s.bar_w), 8);                      // the 8 epilogue warps that fill tensor memory
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
         for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
         fence_barrier_init();
@@ -152,8 +157,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         // Warp pw owns edges 8 pw .. 8 pw + 7 of every tile; a lane owns 8 channels (128-bit loads / stores).
         //   * pq is pre-scaled by 1/2 (api.cu), wr / wd are halved here: hv = Pa' + Pb' + r2 wr' + d0 wd' feeds
         //     SiLU(2 hv) = hv + hv tanh(hv) directly (FADD, 2 FFMA, MUFU, FFMA per element).
-        //   * Pb rows stream through an 8-slot register pipeline (no L1 allocation): the slot of edge i is refilled
-        //     with edge i of the NEXT tile right after edge i is computed, so a gather has a whole tile to land.
+        //   * Pb rows (512 B of f16) stream through an 8-slot register pipeline (no L1 allocation): the slot of
+        //     edge i is refilled with edge i of the NEXT tile right after edge i is computed, so a gather has a
+        //     whole tile to land.  Pa + Pb is added in f16x2, widened once, the rest of the layer runs in fp32.
         //   * Pa changes once per CSR row run: a warp-uniform branch reloads it; the rows a tile will need are
         //     pulled into L1 one tile ahead (one 32-sector touch per row), so the reload is an L1 hit.
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
@@ -165,11 +171,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 #pragma unroll
         for (int k = 0; k < 8; ++k) { wr[k] *= 0.5f; wd[k] *= 0.5f; }
         const uint32_t ldp = (uint32_t)a.ldp;                                            // row index * ldp fits 32 bits (checked at launch)
-        const float* pa_base = a.p + a.off_a + 8 * lane;
-        const float* pb_base = a.p + a.off_b + 8 * lane;
-        const float* pa_touch = pa_base;                                                 // lane l touches sector l of a 1 KB row
-        const uint32_t x_lane = smem_u32(s.x[0]) + (uint32_t)(((lane >> 3) << 13) | (pw << 10) | ((lane & 7) << 4));
-
+        const __half* pq = reinterpret_cast<const __half*>(a.p);                         // f16 rows, pre-scaled by 1/2 (tc_node.cu)
+        const __half* pa_base = pq + a.off_a + 8 * lane;
+        const __half* pb_base = pq + a.off_b + 8 * lane;
+        const __half* pa_touch = pq + a.off_a + 16 * (lane & 15);                        // lanes 0-15 touch the 16 sectors of a 512 B row
         // Edges past E (last tile only) are processed as edge (0, 0): finite garbage in columns nobody reads.
         int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
         auto load_rc = [&](int it, int& r, int& c, float& d0) {
@@ -177,17 +182,19 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             r = 0; c = 0; d0 = 0.f;
             if (it < my_tiles && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
         };
-        // L1 prefetch of the distinct rows of a group: one cp.async.ca per row, lane l pulling sector l of the
-        // 1 KB row through L1 into a scratch word — no destination register, so nothing ever waits on it
+        // L1 prefetch of the distinct rows of a group: one cp.async.ca per row, lane l < 16 pulling sector l of the
+        // 512 B row through L1 into a scratch word — no destination register, so nothing ever waits on it
         const uint32_t scratch = smem_u32(&s.touch[pw][lane]);
         auto touch_rows = [&](int rows_on_lanes) {
             const int prev = __shfl_up_sync(0xffffffffu, rows_on_lanes, 1);
-            unsigned fm = __ballot_sync(0xffffffffu, lane < 8 && (lane == 0 || rows_on_lanes != prev));
+            const unsigned fm0 = __ballot_sync(0xffffffffu, lane < 8 && (lane == 0 || rows_on_lanes != prev));
+            unsigned fm = fm0;
             while (fm) {
                 const int i = __ffs(fm) - 1;
                 fm &= fm - 1;
                 const int r = __shfl_sync(0xffffffffu, rows_on_lanes, i);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(pa_touch + (uint32_t)r * ldp) : "memory");
+                if (lane < 16)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(pa_touch + (uint32_t)r * ldp) : "memory");
             }
         };
         // metadata runs two tiles ahead: m_ = this tile (complete), n_ = next tile (r2 pending), f_ = loading
@@ -202,16 +209,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         if (m_row < a.n_moving || m_col < a.n_moving)                                    // an endpoint moved since the graph build
             m_r2 = dist2(a.x[3 * m_row], a.x[3 * m_row + 1], a.x[3 * m_row + 2], a.x[3 * m_col], a.x[3 * m_col + 1], a.x[3 * m_col + 2]);
         touch_rows(m_row);
-        float4 pb[8][2];
+        uint4 pb[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {                                                    // fill the pipeline: the first tile
-            const int c = __shfl_sync(0xffffffffu, m_col, u);
-            const float* rb = pb_base + (uint32_t)c * ldp;
-            pb[u][0] = ldg_na(rb); pb[u][1] = ldg_na(rb + 4);
-        }
-        float cur[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cur[k] = 0.f;
+        for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile
+            pb[u] = ldg_na_u4(pb_base + (uint32_t)__shfl_sync(0xffffffffu, m_col, u) * ldp);
+        uint4 cur = make_uint4(0u, 0u, 0u, 0u);                                          // Pa of the current CSR row run (8 halves)
         int cur_row = -1;
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
         const int l74 = (lane & 7) << 4;
@@ -236,19 +238,23 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 const int row = __shfl_sync(0xffffffffu, m_row, i);
                 const float r2 = __shfl_sync(0xffffffffu, m_r2, i);
                 const float d0 = __shfl_sync(0xffffffffu, m_d0, i);
-                ldg8_if(cur, pa_base + (uint32_t)row * ldp, row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
+                ldg4_if(cur, pa_base + (uint32_t)row * ldp, row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
                 cur_row = row;
-                float vb[8], y[8];
-                unpack8(pb[i][0], pb[i][1], vb);
+                float y[8];
+                {
+                    const uint32_t ca[4] = {cur.x, cur.y, cur.z, cur.w}, cb[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    y[k] = silu_half<FMT>(fmaf(d0, wd[k], fmaf(r2, wr[k], cur[k] + vb[k])));
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ca[k2]), *reinterpret_cast<const __half2*>(&cb[k2]));
+                        const float2 f = __half22float2(sum);
+                        y[2 * k2] = silu_half<FMT>(fmaf(d0, wd[2 * k2], fmaf(r2, wr[2 * k2], f.x)));
+                        y[2 * k2 + 1] = silu_half<FMT>(fmaf(d0, wd[2 * k2 + 1], fmaf(r2, wr[2 * k2 + 1], f.y)));
+                    }
+                }
                 *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) =            // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
                     make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
                 // refill the slot with the same edge of the next tile
-                const int c = __shfl_sync(0xffffffffu, n_col, i);
-                const float* rb = pb_base + (uint32_t)c * ldp;
-                pb[i][0] = ldg_na(rb); pb[i][1] = ldg_na(rb + 4);
+                pb[i] = ldg_na_u4(pb_base + (uint32_t)__shfl_sync(0xffffffffu, n_col, i) * ldp);
             }
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
             fence_proxy_async();                                                        // generic-proxy writes -> async proxy
@@ -262,10 +268,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ epilogue ================================
-        static_assert(REGS_EPILOGUE == 96, "the epilogue keeps its launch allocation");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
         const int ew = wid, q = ew & 3, gi = ew >> 2;
         const int c0 = 32 * q + lane, c1 = c0 + 128;                                     // this thread's two channels
-        const float hb0 = 0.5f * a.b2[c0], hb1 = 0.5f * a.b2[c1];         // SiLU(v + b) from hv = v / 2 + b / 2
+        const float hb0 = 0.5f * a.b2[c0], hb1 = 0.5f * a.b2[c1];                        // SiLU(v + b) from hv = v / 2 + b / 2
         const bool gated = a.coord || a.attention;
         const float wv0 = gated ? a.wv[c0] : 0.f, wv1 = gated ? a.wv[c1] : 0.f;
         static_assert(H == 256, "segment stores shift by 8");
@@ -273,27 +279,22 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* out1 = a.agg + c1;
         float* redw = s.red[ew];
         float* gatew = s.gate[ew];
-        if (my_tiles > 0) {
-            // resident weights: thread (q, lane) of group gi owns row c = 128 gi + 32 q + lane of the [out][in]
+        const int l16 = lane & 15, g16 = lane >> 4;
+        if (my_tiles > 0 && gi < 2) {
+            // resident weights: thread (q, lane) of groups 0 / 1 owns row c = 128 gi + 32 q + lane of the [out][in]
             // matrix = TMEM lane 32 q + lane of M-half gi.  Its 256 K elements are read from the swizzled panel
             // image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 128 packed 32-bit columns.
             const int r = 128 * gi + 32 * q + lane;
 #pragma unroll 1
-            for (int kp = 0; kp < 4; kp += 2) {                                          // two panels (16 loads per thread) in flight
+            for (int kp = 0; kp < 4; ++kp) {
                 const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
-                uint32_t wa[32], wb[32];
+                uint32_t wa[32];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
                     wa[4 * c] = t.x; wa[4 * c + 1] = t.y; wa[4 * c + 2] = t.z; wa[4 * c + 3] = t.w;
                 }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 t = *reinterpret_cast<const uint4*>(src + W_PANEL_BYTES + ((c ^ (r & 7)) << 4));
-                    wb[4 * c] = t.x; wb[4 * c + 1] = t.y; wb[4 * c + 2] = t.z; wb[4 * c + 3] = t.w;
-                }
                 tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32, wa);
-                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32 + 32, wb);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -303,83 +304,77 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
             const int tile = blockIdx.x + it * gridDim.x;
-            const int u0 = tile * TILE + 32 * gi;                                        // first edge of this group's unit
-            const int my_dst = (!a.coord && u0 + lane < E) ? a.edst[u0 + lane] : -1;
+            const int u0 = tile * TILE + GROUP_EDGES * gi;                               // first edge of this group's unit
+            const int my_dst = (!a.coord && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
             mbar_wait(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 1);
-            float v0[32], v1[32];
+            float v0[16], v1[16];
             {
-                uint32_t r0[32], r1[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + ts * TS_COLS + 32 * gi;
-                tmem_ld32_issue(taddr, r0);
-                tmem_ld32_issue(taddr + TILE, r1);
+                uint32_t r0[16], r1[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + ts * TS_COLS + GROUP_EDGES * gi;
+                tmem_ld16_issue(taddr, r0);
+                tmem_ld16_issue(taddr + TILE, r1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { v0[j] = __uint_as_float(r0[j]); v1[j] = __uint_as_float(r1[j]); }
+                for (int j = 0; j < 16; ++j) { v0[j] = __uint_as_float(r0[j]); v1[j] = __uint_as_float(r1[j]); }
             }
             tc_fence_before();                                                           // this warp's share of the stage is drained
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v0[j] = silu_half<FMT>(fmaf(0.5f, v0[j], hb0)); v1[j] = silu_half<FMT>(fmaf(0.5f, v1[j], hb1)); }
+            for (int j = 0; j < 16; ++j) { v0[j] = silu_half<FMT>(fmaf(0.5f, v0[j], hb0)); v1[j] = silu_half<FMT>(fmaf(0.5f, v1[j], hb1)); }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 3);
             float gate = 1.f;
             if (gated) {
                 // sum over the 256 channels of wv[c] * m[c, edge]: the thread's two channels are added in
                 // registers, the warp's 32 lanes through a transposed pass over shared memory (thread = channel
-                // pair writes a row, thread = edge sums a column), the group's 4 warps through s.part
-                const int g = lane >> 4, l16 = lane & 15;
-                float tot2[2];
+                // pair writes a row of 16 edges, thread = (edge, row half) sums a column), the group's 4 warps
+                // through s.part
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const int j = 16 * hh + 4 * j4;
-                        *reinterpret_cast<float4*>(redw + lane * RED_STRIDE + 4 * j4) =
-                            make_float4(fmaf(wv1, v1[j], wv0 * v0[j]), fmaf(wv1, v1[j + 1], wv0 * v0[j + 1]),
-                                        fmaf(wv1, v1[j + 2], wv0 * v0[j + 2]), fmaf(wv1, v1[j + 3], wv0 * v0[j + 3]));
-                    }
-                    __syncwarp();
-                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {                                     // bank-conflict-free split of the 32 rows
-                        const int k = 8 * kk + 4 * g;
-                        t0 += redw[k * RED_STRIDE + l16];
-                        t1 += redw[(k + 1) * RED_STRIDE + l16];
-                        t2 += redw[(k + 2) * RED_STRIDE + l16];
-                        t3 += redw[(k + 3) * RED_STRIDE + l16];
-                    }
-                    float t = (t0 + t1) + (t2 + t3);
-                    t += __shfl_xor_sync(0xffffffffu, t, 16);
-                    tot2[hh] = t;
-                    __syncwarp();
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const int j = 4 * j4;
+                    *reinterpret_cast<float4*>(redw + lane * RED_STRIDE + j) =
+                        make_float4(fmaf(wv1, v1[j], wv0 * v0[j]), fmaf(wv1, v1[j + 1], wv0 * v0[j + 1]),
+                                    fmaf(wv1, v1[j + 2], wv0 * v0[j + 2]), fmaf(wv1, v1[j + 3], wv0 * v0[j + 3]));
                 }
+                __syncwarp();
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {                                         // bank-conflict-free split of the 32 rows
+                    const int k = 8 * kk + 4 * g16;
+                    t0 += redw[k * RED_STRIDE + l16];
+                    t1 += redw[(k + 1) * RED_STRIDE + l16];
+                    t2 += redw[(k + 2) * RED_STRIDE + l16];
+                    t3 += redw[(k + 3) * RED_STRIDE + l16];
+                }
+                float t = (t0 + t1) + (t2 + t3);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
                 const int pbuf = it & 1;
-                s.part[pbuf][ew][lane] = g ? tot2[1] : tot2[0];                             // lane = edge inside the unit
+                if (lane < GROUP_EDGES) s.part[pbuf][ew][lane] = t;                       // lane = edge inside the unit
                 if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 4);
                 named_bar_sync(1 + gi, 4 * 32);
                 if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 5);
-                const float tot = a.bv + ((s.part[pbuf][4 * gi][lane] + s.part[pbuf][4 * gi + 1][lane]) +
-                                          (s.part[pbuf][4 * gi + 2][lane] + s.part[pbuf][4 * gi + 3][lane]));
+                const float tot = a.bv + ((s.part[pbuf][4 * gi][l16] + s.part[pbuf][4 * gi + 1][l16]) +
+                                          (s.part[pbuf][4 * gi + 2][l16] + s.part[pbuf][4 * gi + 3][l16]));
                 if (a.coord) gate = a.use_tanh ? tanhf(tot) : tot;                       // egnn_new.py:90-93
                 else gate = sigmoid_fast(tot);                                           // egnn_new.py:26-29
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 6);
             if (a.coord) {
-                if (q == 0 && u0 + lane < E) a.escal[u0 + lane] = gate;
+                if (q == 0 && lane < GROUP_EDGES && u0 + lane < E) a.escal[u0 + lane] = gate;
             } else {
                 // segmented sum over the unit's edges: thread = channel pair, registers = edges (two FMA chains)
                 if (gated) {
-                    gatew[lane] = gate;
+                    if (lane < GROUP_EDGES) gatew[lane] = gate;
                     __syncwarp();
                 }
                 const unsigned last_mask = __ballot_sync(0xffffffffu, my_dst >= 0);
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
+                for (int j4 = 0; j4 < 4; ++j4) {
                     float gq[4] = {1.f, 1.f, 1.f, 1.f};
                     if (gated) {
                         const float4 t = *reinterpret_cast<const float4*>(gatew + 4 * j4);

@@ -51,7 +51,7 @@ struct NodeArgs {
     int do_mlp;                                  // 0: projection only (h version 0, straight from the embedding)
     const float* b3; const float* b4;            // node_mlp biases
     const float* bp;                             // projection bias [n_blocks * 256], pre-scaled by 1/2 like the weight image
-    float* pq; int ldp; int n_blocks;            // projection output [N][ldp], n_blocks x 256 channels
+    __half* pq; int ldp; int n_blocks;           // projection output [N][ldp] f16 (pre-scaled by 1/2), n_blocks x 256 channels
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
 };
 
@@ -104,7 +104,7 @@ __device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, 
         *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + u, lane, NX_PANEL)) = pack8<FMT>(f[u][0], f[u][1]);
 }
 
-// Aggregated messages -> tile.  A row whose edges lie inside one 32-edge unit was stored whole (agg[row]);
+// Aggregated messages -> tile.  A row whose edges lie inside one 16-edge unit was stored whole (agg[row]);
 // a row that crosses unit boundaries was stored as per-unit partial sums (see AggView / graph.cu edge_dst):
 // the first two sources of 3 rows are fetched together, longer rows (degree > 32) take a loop.
 // unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a reciprocal multiply.
@@ -144,7 +144,7 @@ __device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a
                           f[u][1].x + f2[u][1].x, f[u][1].y + f2[u][1].y, f[u][1].z + f2[u][1].z, f[u][1].w + f2[u][1].w};
             if (e_[u] > s_[u]) {
                 const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
-                for (int un = uf + 2; un <= ul; ++un) {                               // degree > 32: rare
+                for (int un = uf + 2; un <= ul; ++un) {                               // rows spanning 3+ units (degree > 16)
                     const float* src = g.partials + ((size_t)un * 2) * H + 8 * lane;
                     const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
                     v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             stage_h<FMT>(s.xb, a, n0, wid, lane);
             publish(2);
         }
-        // ---- epilogue 3: projection blocks -> P (fp32)
+        // ---- epilogue 3: projection blocks -> P (f16: halves the edge kernels' gather bytes and staging registers)
         for (int b = 0; b < a.n_blocks; ++b) {
             const int acc = b & 1;
             const float bias = a.bp[b * 256 + ch];
-            float* dst = a.pq + (size_t)(n0 + c0) * a.ldp + (size_t)b * 256 + ch;
+            __half* dst = a.pq + (size_t)(n0 + c0) * a.ldp + (size_t)b * 256 + ch;
             wait_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
 #pragma unroll 1
@@ -344,10 +344,10 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 const int i0 = c0 + 16 * cc;
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
                 if (cc == 2) release_acc(acc);
-                float* d = dst + (size_t)(16 * cc) * a.ldp;
+                __half* d = dst + (size_t)(16 * cc) * a.ldp;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
-                    if (i0 + j < n_valid) *d = v[j] + bias;
+                    if (i0 + j < n_valid) *d = __float2half_rn(v[j] + bias);
             }
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
         }
@@ -380,7 +380,7 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     NodeArgs a{};
     a.h = p.h; a.aggv = av; a.n_rows = p.N; a.do_mlp = v > 0;
     if (v > 0) { a.b3 = W.gcl[v - 1].n0.b; a.b4 = W.gcl[v - 1].n2.b; }
-    a.bp = ps.b_half; a.pq = p.pq; a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
+    a.bp = ps.b_half; a.pq = reinterpret_cast<__half*>(p.pq); a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
     a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;

@@ -27,22 +27,23 @@ t = torch.full((B,), 0.4)
 for _ in range(3):
     h.dynamics_forward(z, xr, t)
 torch.cuda.synchronize()
-n = 4 * 64 * 16
+n = 6 * 64 * 16
 buf = (C.c_longlong * n)()
 h.lib.dp_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
 rc = h.lib.dp_debug_trace(h.h, buf, n)
 assert rc == 0, h.lib.dp_last_error()
-tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(4)]
+tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(6)]
 t0 = min(v for r in tr for it in r for v in it if v > 0)
 names = {0: ["start", "xempty", "half", "-", "-", "-", "arrive", "e0 meta", "e0 pa", "e0 math", "e0 refill", "e1 meta", "e1 pa", "e1 math", "e1 refill"],
          1: ["start", "full", "tempty", "issued"],
          2: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"],
          3: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"]}
+names[4] = names[5] = names[3]
 print("E =", h.flags().last_n_edges, " (cycles relative to the first mark, CTA 0)")
 w = tr[1][63]
 print(f"weights: issue {w[0] - t0}  landed {w[1] - t0}")
 for it in range(10):
-    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue0"), (3, "epilogue1")):
+    for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue0"), (3, "epilogue1"), (4, "epilogue2"), (5, "epilogue3")):
         row = tr[r][it]
         if not any(row):
             continue
