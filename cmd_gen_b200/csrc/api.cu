@@ -112,6 +112,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
         h->tc_mask = atoi(m) ? 3 : 0;
     }
     if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
+    if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
@@ -120,6 +121,9 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
             DP_CUDA(cudaMemset(h->trace, 0, DP_TRACE_WORDS * sizeof(long long)));
         }
     }
+    DP_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    DP_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    DP_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     int rc = egnn_f32_init();
     if (!rc) rc = tc_init();
     if (rc) { delete h; return rc; }
@@ -144,6 +148,9 @@ extern "C" int dp_destroy(dp_handle* h)
     tc_free_weights(h);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->trace) cudaFree(h->trace);
     delete h;
     return DP_OK;
@@ -466,6 +473,7 @@ static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_
 
 static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
 {
+    if (h->skip_mask & (a.coord ? 4 : 1)) return DP_OK;
     prof_begin(h, a.coord ? PROF_EDGE_COORD : PROF_EDGE_MSG, st);
     int rc = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
     prof_end(h, st);
@@ -482,8 +490,17 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     const int S = c.inv_sublayers, G = c.n_layers * S;
     const int unit = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? UNIT_F32 : UNIT_TC;
     int rc = 0;
-    if ((rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
-    if ((rc = launch_build_edges(h, p.x_in, st))) return rc;
+    if (!(h->skip_mask & 32) && (rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
+    // Fork: the radius graph (needs x only) runs on a side branch while the main branch projects the embedded
+    // features (needs h only); they join before the first edge kernel.  Works eagerly and under stream capture
+    // (the side stream joins the capture through the event).  Profiling spans need one stream: no fork then.
+    const bool fork = !h->profile && !(h->skip_mask & 16);
+    if (fork) {
+        DP_CUDA(cudaEventRecord(h->ev_fork, st));
+        DP_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        if ((rc = launch_build_edges(h, p.x_in, h->side_stream))) return rc;
+        DP_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    } else if (!(h->skip_mask & 16) && (rc = launch_build_edges(h, p.x_in, st))) return rc;
     float* x_cur = p.x_a; float* x_next = p.x_b;
 
     auto project = [&](int v) -> int {
@@ -500,12 +517,14 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
 
     const bool fused_node = h->precision != DP_FP32 && (h->tc_mask & 2);
     auto node_phase = [&](int v) -> int {      // tcgen05: node MLP of GCL v-1 + projection of the new h, one launch
+        if (h->skip_mask & 2) return DP_OK;
         prof_begin(h, PROF_NODE, st);
         int e = launch_node_tc(h, v, av, st);
         prof_end(h, st);
         return e;
     };
     if ((rc = fused_node ? node_phase(0) : project(0))) return rc;
+    if (fork) DP_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     for (int i = 0; i < G; ++i) {
         const GclWeights& L = W.gcl[i];
         const ProjSet& pin = W.proj[i];
@@ -544,12 +563,13 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
             prof_begin(h, PROF_EDGE_COORD, st);
-            rc = launch_coord_finish(h, x_cur, x_next, st);
+            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
             prof_end(h, st);
             if (rc) return rc;
             float* t = x_cur; x_cur = x_next; x_next = t;
         }
     }
+    if (h->skip_mask & 32) return DP_OK;
     return launch_decode(h, x_cur, out_phar, out_res, st);
 }
 

@@ -209,6 +209,7 @@ struct dp_handle {
     int sm_count = 148;
     int precision = 0;
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
+    int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
     int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells
     int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
@@ -222,6 +223,8 @@ struct dp_handle {
     int n_steps = 0;
     int64_t launches = 0;
     cudaStream_t capture_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // second branch of a denoiser evaluation: the radius graph runs beside the first projection
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int trace_kernel = 0;              // DIFFPHAR_TRACE: 1 = node kernel, 2 = edge message kernel
     long long* trace = nullptr;        // debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernels (DIFFPHAR_TRACE=1)
     // profiling

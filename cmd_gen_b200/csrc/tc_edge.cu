@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 
     // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
     if (tid == 0) {
-        mbar_init(smem_u32(&s.bar_w), 8);                      // the 8 epilogue warps that fill tensor memory
+        mbar_init(smem_u32(&s.bar_w), EPI_WARPS);              // every epilogue warp fills its share of tensor memory
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
         for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
         fence_barrier_init();
@@ -280,13 +280,14 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* redw = s.red[ew];
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
-        if (my_tiles > 0 && gi < 2) {
-            // resident weights: thread (q, lane) of groups 0 / 1 owns row c = 128 gi + 32 q + lane of the [out][in]
-            // matrix = TMEM lane 32 q + lane of M-half gi.  Its 256 K elements are read from the swizzled panel
-            // image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 128 packed 32-bit columns.
-            const int r = 128 * gi + 32 * q + lane;
+        if (my_tiles > 0) {
+            // resident weights: thread (q, lane) of group gi owns row c = 128 (gi & 1) + 32 q + lane of the [out][in]
+            // matrix = TMEM lane 32 q + lane of M-half gi & 1, K panels 2 (gi >> 1) and 2 (gi >> 1) + 1.  The 128 K
+            // elements are read from the swizzled panel image (chunk c of a row sits at chunk c ^ (row % 8)) and
+            // stored as 64 packed 32-bit columns.  All 16 warps share the fill: two dependent L2 round trips.
+            const int mh = gi & 1, r = 128 * mh + 32 * q + lane;
 #pragma unroll 1
-            for (int kp = 0; kp < 4; ++kp) {
+            for (int kp = 2 * (gi >> 1); kp < 2 * (gi >> 1) + 2; ++kp) {
                 const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
                 uint32_t wa[32];
 #pragma unroll
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                     const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
                     wa[4 * c] = t.x; wa[4 * c + 1] = t.y; wa[4 * c + 2] = t.z; wa[4 * c + 3] = t.w;
                 }
-                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + gi * 128 + kp * 32, wa);
+                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + mh * 128 + kp * 32, wa);
             }
             tmem_st_wait();
             tc_fence_before();

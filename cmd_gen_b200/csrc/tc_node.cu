@@ -23,7 +23,9 @@
 namespace {
 using namespace tc;
 
-constexpr int NT = 96;                           // nodes per tile (UMMA N): 106 CTAs at N = 10 112, and room for a 4-slot ring
+constexpr int NT = 96;                           // tile CAPACITY in nodes (smem / TMEM layout).  A launch uses `stride` <= NT nodes per CTA so that
+                                                 // the tiles fill whole waves of SMs (N = 10 112: 148 CTAs x 69 nodes, not 106 x 96) and an MMA N
+                                                 // of stride rounded up to 16
 constexpr int NX_PANEL = NT * 128;               // 12 KB: 96 nodes x 64 K x 2 B
 constexpr int X_BYTES = 4 * NX_PANEL;            // 48 KB: K = 256
 constexpr int N_WS = 4;                          // weight ring slots (the stream is latency-bound: depth = throughput)
@@ -39,7 +41,7 @@ struct NodeSmem {
     unsigned char xb[X_BYTES];                   // agg tile, later the new-h tile
     unsigned char w[N_WS][W_PANEL_BYTES];        // 128 KB ring
     unsigned long long bar_wfull[N_WS], bar_wempty[N_WS];
-    unsigned long long bar_x[3];                 // B tile ready: [h|agg], t, new h
+    unsigned long long bar_x[4];                 // B tile ready: agg, t, new h, h (GEMM 1 starts on the h half while agg is staged)
     unsigned long long bar_accfull[2], bar_accempty[2];
     uint32_t tmem_holder;
 };
@@ -52,6 +54,9 @@ struct NodeArgs {
     const float* b3; const float* b4;            // node_mlp biases
     const float* bp;                             // projection bias [n_blocks * 256], pre-scaled by 1/2 like the weight image
     __half* pq; int ldp; int n_blocks;           // projection output [N][ldp] f16 (pre-scaled by 1/2), n_blocks x 256 channels
+    int stride; int n_mma;                       // nodes per CTA (<= NT) and the UMMA N that covers them (multiple of 16)
+    int row_block; int n_moving;                 // block `row_block` (row part Qa of the coordinate MLP, -1: none) is only read for rows < n_moving
+                                                 // (update_coords_mask keeps phar rows, dynamics.py:105-107): tiles past them skip it
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
 };
 
@@ -87,14 +92,14 @@ __device__ __forceinline__ uint4 pack8(const float4& f0, const float4& f1)
 // h rows (fp32) -> swizzled 16-bit K-major tile.  Warp w owns rows 6w .. 6w+5 of the tile; lane = 16-byte
 // chunk; all 12 loads of a warp are in flight together.
 template <int FMT>
-__device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane)
+__device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, int n0, int row_end, int wid, int lane)
 {
     float4 f[ROWS_PER_WARP][2];
 #pragma unroll
     for (int u = 0; u < ROWS_PER_WARP; ++u) {
         const int row = n0 + ROWS_PER_WARP * wid + u;
         f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < a.n_rows) {
+        if (row < row_end) {
             const float* src = a.h + (size_t)row * H + 8 * lane;
             f[u][0] = *reinterpret_cast<const float4*>(src); f[u][1] = *reinterpret_cast<const float4*>(src + 4);
         }
@@ -110,7 +115,7 @@ __device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, 
 // unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a reciprocal multiply.
 // `rp` = rowptr[first row of the warp + lane] for lanes 0..6, loaded by the caller ahead of time.
 template <int FMT>
-__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int wid, int lane, int rp)
+__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int row_end, int wid, int lane, int rp)
 {
     const AggView& g = a.aggv;
     const int r0 = n0 + ROWS_PER_WARP * wid;
@@ -123,7 +128,7 @@ __device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a
             const int row = r0 + 3 * hb + u;
             s_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u);
             e_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u + 1);
-            if (row >= a.n_rows) e_[u] = s_[u];
+            if (row >= row_end) e_[u] = s_[u];
             f[u][0] = f[u][1] = f2[u][0] = f2[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e_[u] > s_[u]) {
                 const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
@@ -173,12 +178,13 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     NodeSmem& s = *reinterpret_cast<NodeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n0 = blockIdx.x * NT;
-    const int n_panels = (a.do_mlp ? 12 : 0) + 4 * a.n_blocks;
+    const int n0 = blockIdx.x * a.stride;
+    const int skip_b = (a.row_block >= 0 && n0 >= a.n_moving) ? a.row_block : -1;   // CTA-uniform: all three roles agree
+    const int mlp_panels = a.do_mlp ? 12 : 0;
 
     if (tid == 0) {
         for (int i = 0; i < N_WS; ++i) { mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), 1); }
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s.bar_x[i]), COMPUTE_WARPS);
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.bar_x[i]), COMPUTE_WARPS);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), COMPUTE_WARPS); }
         fence_barrier_init();
     }
@@ -195,23 +201,26 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         // ================================ weight stream ================================
         {
             const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
-            for (int p = 0; p < n_panels; ++p) {
+            int p = 0;                                                                // ring position
+            for (int g = 0; g < mlp_panels + 4 * a.n_blocks; ++g) {                    // g = panel of the image
+                if (g >= mlp_panels && (g - mlp_panels) / 4 == skip_b) continue;
                 const int slot = p % N_WS;
                 if (lane == 0) trace_mark(a.trace, 2, p, 0);
                 mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS) & 1) ^ 1);
                 if (lane == 0) trace_mark(a.trace, 2, p, 1);
                 if (elect_one()) {
                     mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_PANEL_BYTES);
-                    bulk_g2s(w0 + slot * W_PANEL_BYTES, w_img + (size_t)p * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
+                    bulk_g2s(w0 + slot * W_PANEL_BYTES, w_img + (size_t)g * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
                 }
                 __syncwarp();
+                ++p;
             }
         }
     } else if (wid == MMA_WARP) {
         // ================================ MMA issuer ================================
         // the whole warp runs the control flow (uniform: descriptors stay in uniform registers), one elected lane issues
         {
-            constexpr uint32_t idesc = make_idesc(FMT, 128, NT);
+            const uint32_t idesc = make_idesc(FMT, 128, a.n_mma);
             const uint32_t td = warp_uniform(tmem_base);
             const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
             const uint32_t xa = warp_uniform(smem_u32(s.xa)), xb = warp_uniform(smem_u32(s.xb));
@@ -219,11 +228,12 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             int p = 0;
             int acc_uses[2] = {0, 0};
             auto run_gemm = [&](int acc, uint32_t x0, uint32_t x1, int k_panels) {
-                // x0: first 4 panels' tile, x1: panels 4-7 (K = 512 only)
+                // x0: first 4 panels' tile, x1: panels 4-7 (K = 512 only: the agg half, staged after the h half)
                 if (acc_uses[acc] > 0) mbar_wait(smem_u32(&s.bar_accempty[acc]), (acc_uses[acc] - 1) & 1);
                 tc_fence_after();
                 for (int kp = 0; kp < k_panels; ++kp, ++p) {
                     const int slot = p % N_WS;
+                    if (kp == 4) mbar_wait(smem_u32(&s.bar_x[0]), 0);
                     if (tr) trace_mark(a.trace, 1, p, 0);
                     mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS) & 1);
                     if (tr) trace_mark(a.trace, 1, p, 1);
@@ -240,19 +250,23 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 acc_uses[acc] += 1;
             };
             if (a.do_mlp) {
-                mbar_wait(smem_u32(&s.bar_x[0]), 0);
+                mbar_wait(smem_u32(&s.bar_x[3]), 0);
                 run_gemm(0, xa, xb, 8);
                 mbar_wait(smem_u32(&s.bar_x[1]), 0);
                 run_gemm(1, xa, 0, 4);
             }
             mbar_wait(smem_u32(&s.bar_x[2]), 0);
-            for (int b = 0; b < a.n_blocks; ++b) run_gemm(b & 1, xb, 0, 4);
+            for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
+                if (b == skip_b) continue;
+                run_gemm(cnt & 1, xb, 0, 4);
+                ++cnt;
+            }
         }
     } else {
         // ================================ compute warps ================================
         // epilogue mapping: warp = (TMEM lane quarter q, channel half, 48-column half of the tile);
         // thread = one output channel, registers = 16 node columns per tcgen05.ld
-        const int q = wid & 3, g = wid >> 2, half = g >> 1, c0 = COLS_PER_WARP * (g & 1);
+        const int q = wid & 3, g = wid >> 2, half = g >> 1, cpar = g & 1;
         const int ch = 128 * half + 32 * q + lane;
         const uint32_t t_lane = (uint32_t)(32 * q) << 16;
         int acc_uses[2] = {0, 0};
@@ -274,23 +288,27 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         const bool tr = wid == 0 && lane == 0;
         pdl_wait();
         if (tr) trace_mark(a.trace, 0, 0, 0);
-        const int n_valid = a.n_rows - n0;                                          // rows of this tile that exist
+        const int n_valid = min(a.stride, a.n_rows - n0);                            // rows of this tile that exist
         if (a.do_mlp) {
             int rp = 0;                                                              // CSR bounds of the warp's rows: issued first
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
-            stage_h<FMT>(s.xa, a, n0, wid, lane);
+            stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
+            publish(3);
             if (tr) trace_mark(a.trace, 0, 0, 1);
-            stage_agg<FMT>(s.xb, a, n0, wid, lane, rp);
+            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp);
             publish(0);
             if (tr) trace_mark(a.trace, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> xa (the n0 MMAs have all retired: acc_full follows them)
+            // A warp takes every other 16-column chunk (i0 = 16 (2 cc + cpar)), so both warps of a channel half stay
+            // busy whatever the tile's node count; chunks past the tile's last node are skipped.
             const float b3c = a.b3[ch];
             wait_acc(0);
             if (tr) trace_mark(a.trace, 0, 0, 3);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
+                const int i0 = 16 * (2 * cc + cpar);
+                if (i0 >= n_valid) break;
                 float v[16];
-                const int i0 = c0 + 16 * cc;
                 tmem_ld16(tmem_base + t_lane + half * NT + i0, v);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) store_k16<FMT>(s.xa, i0 + j, ch, silu_tc<FMT>(v[j] + b3c));
@@ -300,25 +318,26 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             if (tr) trace_mark(a.trace, 0, 0, 4);
             // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> xb
             const float b4c = a.b4[ch];
-            float* hrow = a.h + (size_t)(n0 + c0) * H + ch;
+            float* hrow = a.h + (size_t)n0 * H + ch;
             float r[16];                                                             // residual rows of chunk 0: fetched under the MMAs
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = (c0 + j < n_valid) ? hrow[(size_t)j * H] : 0.f;
+            for (int j = 0; j < 16; ++j) r[j] = (16 * cpar + j < n_valid) ? hrow[(size_t)(16 * cpar + j) * H] : 0.f;
             wait_acc(1);
             if (tr) trace_mark(a.trace, 0, 0, 5);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
+                const int i0 = 16 * (2 * cc + cpar);
+                if (i0 >= n_valid) break;
                 float v[16], rn[16];
-                const int i0 = c0 + 16 * cc;
                 tmem_ld16(tmem_base + ACC_COLS + t_lane + half * NT + i0, v);
                 if (cc < 2) {                                                        // next chunk's residual rows
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) rn[j] = (i0 + 16 + j < n_valid) ? hrow[(size_t)(16 * cc + 16 + j) * H] : 0.f;
+                    for (int j = 0; j < 16; ++j) rn[j] = (i0 + 32 + j < n_valid) ? hrow[(size_t)(i0 + 32 + j) * H] : 0.f;
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float o = r[j] + (v[j] + b4c);
-                    if (i0 + j < n_valid) hrow[(size_t)(16 * cc + j) * H] = o;
+                    if (i0 + j < n_valid) hrow[(size_t)(i0 + j) * H] = o;
                     store_k16<FMT>(s.xb, i0 + j, ch, (i0 + j < n_valid) ? o : 0.f);
                 }
 #pragma unroll
@@ -328,27 +347,30 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             publish(2);
             if (tr) trace_mark(a.trace, 0, 0, 6);
         } else {
-            stage_h<FMT>(s.xb, a, n0, wid, lane);
+            stage_h<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane);
             publish(2);
         }
         // ---- epilogue 3: projection blocks -> P (f16: halves the edge kernels' gather bytes and staging registers)
-        for (int b = 0; b < a.n_blocks; ++b) {
-            const int acc = b & 1;
+        for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
+            if (b == skip_b) continue;
+            const int acc = cnt & 1;
+            ++cnt;
             const float bias = a.bp[b * 256 + ch];
-            __half* dst = a.pq + (size_t)(n0 + c0) * a.ldp + (size_t)b * 256 + ch;
+            __half* dst = a.pq + (size_t)n0 * a.ldp + (size_t)b * 256 + ch;
             wait_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
+                const int i0 = 16 * (2 * cc + cpar);
+                if (i0 >= n_valid) break;
                 float v[16];
-                const int i0 = c0 + 16 * cc;
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
-                if (cc == 2) release_acc(acc);
-                __half* d = dst + (size_t)(16 * cc) * a.ldp;
+                __half* d = dst + (size_t)i0 * a.ldp;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
                     if (i0 + j < n_valid) *d = __float2half_rn(v[j] + bias);
             }
+            release_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
         }
     }
@@ -381,10 +403,16 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     a.h = p.h; a.aggv = av; a.n_rows = p.N; a.do_mlp = v > 0;
     if (v > 0) { a.b3 = W.gcl[v - 1].n0.b; a.b4 = W.gcl[v - 1].n2.b; }
     a.bp = ps.b_half; a.pq = reinterpret_cast<__half*>(p.pq); a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
+    a.row_block = ps.off_coord >= 0 ? ps.off_coord / 256 : -1; a.n_moving = p.Np;
     a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;
-    const int grid = (p.N + NT - 1) / NT;
+    // whole waves of SMs: the fewest waves that fit NT-node tiles, then the smallest stride that keeps that count
+    const int waves = (p.N + NT * h->sm_count - 1) / (NT * h->sm_count);
+    int stride = (p.N + waves * h->sm_count - 1) / (waves * h->sm_count);
+    if (stride < 16) stride = 16;
+    a.stride = stride; a.n_mma = (stride + 15) / 16 * 16;
+    const int grid = (p.N + stride - 1) / stride;
     const int smem = (int)sizeof(NodeSmem) + 1024;
     const unsigned char* img = h->tc->node[v].img[fmt];
     if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
