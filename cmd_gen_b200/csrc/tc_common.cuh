@@ -47,6 +47,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// Wait of a role that is usually early (epilogue / producer warps): the poll loop of 16-24 waiting warps would
+// otherwise eat a seventh of the SM's issue slots; try_wait may suspend up to the hint, then the warp backs off.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+        if (!ok) __nanosleep(64);
+    } while (!ok);
+}
+// base + index * stride_bytes in ONE instruction (IMAD.WIDE.U32): gather addresses without 64-bit add chains
+__device__ __forceinline__ const void* row_ptr(const void* base, uint32_t index, uint32_t stride_bytes)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(index), "r"(stride_bytes), "l"(reinterpret_cast<unsigned long long>(base)));
+    return reinterpret_cast<const void*>(r);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { wr[k] *= 0.5f; wd[k] *= 0.5f; }
-        const uint32_t ldp = (uint32_t)a.ldp;                                            // row index * ldp fits 32 bits (checked at launch)
+        const uint32_t ldp_b = 2u * (uint32_t)a.ldp;                                     // row stride in bytes (f16 rows)
         const __half* pq = reinterpret_cast<const __half*>(a.p);                         // f16 rows, pre-scaled by 1/2 (tc_node.cu)
         const __half* pa_base = pq + a.off_a + 8 * lane;
         const __half* pb_base = pq + a.off_b + 8 * lane;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 fm &= fm - 1;
                 const int r = __shfl_sync(0xffffffffu, rows_on_lanes, i);
                 if (lane < 16)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(pa_touch + (uint32_t)r * ldp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(row_ptr(pa_touch, (uint32_t)r, ldp_b)) : "memory");
             }
         };
         // metadata runs two tiles ahead: m_ = this tile (complete), n_ = next tile (r2 pending), f_ = loading
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         uint4 pb[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile
-            pb[u] = ldg_na_u4(pb_base + (uint32_t)__shfl_sync(0xffffffffu, m_col, u) * ldp);
+            pb[u] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, m_col, u), ldp_b));
         uint4 cur = make_uint4(0u, 0u, 0u, 0u);                                          // Pa of the current CSR row run (8 halves)
         int cur_row = -1;
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const float xr0 = a.x[xr_i], xr1 = a.x[xr_i + 1], xr2 = a.x[xr_i + 2];
             const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
             touch_rows(n_row);
-            mbar_wait(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
+            mbar_wait_relaxed(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
             unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 const int row = __shfl_sync(0xffffffffu, m_row, i);
                 const float r2 = __shfl_sync(0xffffffffu, m_r2, i);
                 const float d0 = __shfl_sync(0xffffffffu, m_d0, i);
-                ldg4_if(cur, pa_base + (uint32_t)row * ldp, row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
+                ldg4_if(cur, row_ptr(pa_base, (uint32_t)row, ldp_b), row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
                 cur_row = row;
                 float y[8];
                 {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) =            // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
                     make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
                 // refill the slot with the same edge of the next tile
-                pb[i] = ldg_na_u4(pb_base + (uint32_t)__shfl_sync(0xffffffffu, n_col, i) * ldp);
+                pb[i] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, n_col, i), ldp_b));
             }
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
             fence_proxy_async();                                                        // generic-proxy writes -> async proxy
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const int u0 = tile * TILE + GROUP_EDGES * gi;                               // first edge of this group's unit
             const int my_dst = (!a.coord && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
-            mbar_wait(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
+            mbar_wait_relaxed(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 1);
             float v0[16], v1[16];
