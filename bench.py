@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DIFFPHAR_PRECISION", "bf16"),
-                    choices=["fp32", "tf32", "bf16", "f16"])
+                    choices=["fp32", "tf32", "bf16", "f16", "f16fast", "f16fast32"])
     ap.add_argument("--timesteps", type=int, default=WORKLOAD["T"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))

@@ -12,7 +12,9 @@ from __future__ import annotations
 from dataclasses import dataclass, asdict
 from typing import List, Tuple
 
-PRECISION_MODES = {"fp32": 0, "tf32": 1, "bf16": 2, "f16": 3}
+# "f16fast": f16 operands, packed f16x2 first layer + tanh-form SiLU in the edge kernels (bench default);
+# "f16fast32": its A/B variant with the producer's tanh in fp32
+PRECISION_MODES = {"fp32": 0, "tf32": 1, "bf16": 2, "f16": 3, "f16fast": 4, "f16fast32": 5}
 
 
 @dataclass(frozen=True)

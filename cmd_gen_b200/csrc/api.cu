@@ -93,7 +93,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
              DP_ERR_INVALID, "phar_nf/residue_nf must be in [1,64]");
     DP_CHECK(cfg->joint_nf > 0 && cfg->joint_nf <= 64, DP_ERR_INVALID, "joint_nf must be in [1,64]");
     DP_CHECK(cfg->n_layers > 0 && cfg->inv_sublayers > 0, DP_ERR_INVALID, "n_layers/inv_sublayers must be positive");
-    DP_CHECK(cfg->precision >= DP_FP32 && cfg->precision <= DP_F16, DP_ERR_INVALID, "unknown precision %d", cfg->precision);
+    DP_CHECK(cfg->precision >= DP_FP32 && cfg->precision <= DP_F16_FAST32, DP_ERR_INVALID, "unknown precision %d", cfg->precision);
     int n = 0;
     DP_CUDA(cudaGetDeviceCount(&n));
     DP_CHECK(device >= 0 && device < n, DP_ERR_INVALID, "device %d out of range (%d visible)", device, n);
@@ -325,7 +325,7 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
 extern "C" int dp_set_precision(dp_handle* h, int precision)
 {
     DP_CHECK(h, DP_ERR_INVALID, "null handle");
-    DP_CHECK(precision >= DP_FP32 && precision <= DP_F16, DP_ERR_INVALID, "unknown precision %d", precision);
+    DP_CHECK(precision >= DP_FP32 && precision <= DP_F16_FAST32, DP_ERR_INVALID, "unknown precision %d", precision);
     h->precision = precision;
     return DP_OK;
 }
@@ -532,7 +532,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
         e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
-        e.edst = p.edst; e.n_moving = p.Np;
+        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
         e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
@@ -558,7 +558,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
             q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
-            q.edst = p.edst; q.n_moving = p.Np;
+            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;

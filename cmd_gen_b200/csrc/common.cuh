@@ -266,6 +266,7 @@ struct EdgeArgs {
     const int* edst;                                 // per-edge segmented-sum destination (graph.cu), tcgen05 path
     int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
+    int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)
     int coord; int attention; int use_tanh;

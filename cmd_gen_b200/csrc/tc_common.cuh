@@ -14,6 +14,16 @@
 namespace tc {
 
 constexpr int FMT_F16 = 0, FMT_BF16 = 1;
+// Arithmetic mode of the edge kernel (operand format + how the CUDA cores compute around the MMA):
+//   MODE_F16  : f16 operands, fp32 first layer, SiLU with ex2 / rcp (~1e-7)           DP_F16   "TF32-class" accuracy
+//   MODE_BF16 : bf16 operands, fp32 first layer, SiLU with one tanh.approx.f32         DP_BF16
+//   MODE_F16P : f16 operands, first layer in PACKED f16x2 (HADD2 / HFMA2, two channels per instruction, SiLU with
+//               tanh.approx.f16x2), fp32 tanh SiLU in the epilogue                     DP_F16_FAST (bench default)
+//   MODE_F16Q : as MODE_F16P but the producer's tanh runs in fp32 (A/B of the MUFU.TANH.F16 rate)   DP_F16_FAST32
+constexpr int MODE_F16 = 0, MODE_BF16 = 1, MODE_F16P = 2, MODE_F16Q = 3;
+__host__ __device__ constexpr int fmt_of_mode(int mode) { return mode == MODE_BF16 ? FMT_BF16 : FMT_F16; }
+// which SiLU flavour silu_half<> / silu_tc<> use: every mode but the accurate f16 one takes the one-MUFU tanh form
+__host__ __device__ constexpr int silu_of_mode(int mode) { return mode == MODE_F16 ? FMT_F16 : FMT_BF16; }
 constexpr int PANEL_K = 64;                 // 16-bit elements per 128-byte swizzle row
 constexpr int W_PANEL_BYTES = 256 * 128;    // 256 out channels x 128 B (one K panel of a 256-channel block)
 
@@ -264,6 +274,13 @@ __device__ __forceinline__ float tanh_approx(float v)
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+// two f16 lanes at once: MUFU.TANH.F16 on each half + one PRMT (max abs error 2^-10.987)
+__device__ __forceinline__ __half2 tanh_approx_h2(__half2 v)
+{
+    uint32_t r;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&v)));
+    return *reinterpret_cast<__half2*>(&r);
 }
 __device__ __forceinline__ float ex2_approx(float v)
 {

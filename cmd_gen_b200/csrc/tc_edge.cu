@@ -95,11 +95,16 @@ __device__ __forceinline__ void trace_mark_t(long long* trace, int role, int it,
 }
 #define trace_mark(tr, role, it, slot) trace_mark_t<TRACE>(tr, role, it, slot)
 
-template <int FMT, bool TRACE>
+template <int MODE, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const unsigned char* __restrict__ w_img)
 {
+    constexpr int FMT = fmt_of_mode(MODE);            // operand format of the MMA
+    constexpr int SFMT = silu_of_mode(MODE);          // SiLU flavour of the fp32 paths
+    constexpr bool PACKED = MODE == MODE_F16P || MODE == MODE_F16Q;   // first layer in f16x2
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // offset arithmetic on the shared array itself (not through an integer cast): the compiler keeps the shared
+    // state space and emits STS / LDS with 32-bit addresses instead of generic ST.E / LD.E
+    unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     EdgeSmem& s = *reinterpret_cast<EdgeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
@@ -119,6 +124,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     static_assert(W_COLS + N_TS * TS_COLS <= TMEM_COLS, "tensor memory budget");
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
+    // The producers' first-tile metadata does not wait for the edge count: loaded speculatively (the arrays hold
+    // ecap entries) and masked once E has arrived — one L2 round trip less in the pipeline fill
+    int s_row = 0, s_col = 0; float s_d0 = 0.f;
+    if (wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+        const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
+        if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
+    }
     const int E = *a.n_edges;
     const int n_tiles = (E + TILE - 1) / TILE;
     const int my_tiles = max(0, (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);   // 0: idle CTA, falls through
@@ -170,6 +182,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { wr[k] *= 0.5f; wd[k] *= 0.5f; }
+        // packed modes: the same eight halved weights as four f16x2 pairs (the fp32 copies are dead then)
+        __half2 wr2[4], wd2[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            wr2[k2] = __floats2half2_rn(wr[2 * k2], wr[2 * k2 + 1]);
+            wd2[k2] = __floats2half2_rn(wd[2 * k2], wd[2 * k2 + 1]);
+        }
         const uint32_t ldp_b = 2u * (uint32_t)a.ldp;                                     // row stride in bytes (f16 rows)
         const __half* pq = reinterpret_cast<const __half*>(a.p);                         // f16 rows, pre-scaled by 1/2 (tc_node.cu)
         const __half* pa_base = pq + a.off_a + 8 * lane;
@@ -203,16 +222,19 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
         };
         int n_row, n_col; float n_d0;
-        load_rc(0, m_row, m_col, m_d0);
+        {
+            const bool ok = my_tiles > 0 && lane < 8 && (int)blockIdx.x * TILE + 8 * pw + lane < E;   // the speculative loads were real edges
+            m_row = ok ? s_row : 0; m_col = ok ? s_col : 0; m_d0 = ok ? s_d0 : 0.f;
+        }
+        uint4 pb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile's gathers go out first
+            pb[u] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, m_col, u), ldp_b));
+        touch_rows(m_row);
         load_rc(1, n_row, n_col, n_d0);
         m_r2 = m_d0;
         if (m_row < a.n_moving || m_col < a.n_moving)                                    // an endpoint moved since the graph build
             m_r2 = dist2(a.x[3 * m_row], a.x[3 * m_row + 1], a.x[3 * m_row + 2], a.x[3 * m_col], a.x[3 * m_col + 1], a.x[3 * m_col + 2]);
-        touch_rows(m_row);
-        uint4 pb[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile
-            pb[u] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, m_col, u), ldp_b));
         uint4 cur = make_uint4(0u, 0u, 0u, 0u);                                          // Pa of the current CSR row run (8 halves)
         int cur_row = -1;
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
@@ -232,27 +254,50 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             mbar_wait_relaxed(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
             unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
+            uint32_t m_rd = 0u;
+            if (PACKED) {                                                               // (r2, d0) of the lane's edge as one f16x2 word
+                const __half2 t = __floats2half2_rn(fminf(m_r2, 60000.f), fminf(m_d0, 60000.f));
+                m_rd = *reinterpret_cast<const uint32_t*>(&t);
+            }
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = __shfl_sync(0xffffffffu, m_row, i);
-                const float r2 = __shfl_sync(0xffffffffu, m_r2, i);
-                const float d0 = __shfl_sync(0xffffffffu, m_d0, i);
                 ldg4_if(cur, row_ptr(pa_base, (uint32_t)row, ldp_b), row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
                 cur_row = row;
-                float y[8];
-                {
-                    const uint32_t ca[4] = {cur.x, cur.y, cur.z, cur.w}, cb[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
+                const uint32_t ca[4] = {cur.x, cur.y, cur.z, cur.w}, cb[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
+                uint32_t o[4];
+                if (PACKED) {
+                    // two channels per instruction: (Pa' + Pb') + r2 wr' + d0 wd' and SiLU(2 hv) = hv + hv tanh(hv) in
+                    // f16x2; (r2, d0) travel as one packed word, the halves are broadcast by the operand selectors
+                    const uint32_t rd = __shfl_sync(0xffffffffu, m_rd, i);
+                    const __half2 r2h = __low2half2(*reinterpret_cast<const __half2*>(&rd));
+                    const __half2 d0h = __high2half2(*reinterpret_cast<const __half2*>(&rd));
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ca[k2]), *reinterpret_cast<const __half2*>(&cb[k2]));
+                        const __half2 hv = __hfma2(d0h, wd2[k2], __hfma2(r2h, wr2[k2], sum));
+                        __half2 y2;
+                        if (MODE == MODE_F16P) {
+                            y2 = __hfma2(hv, tanh_approx_h2(hv), hv);
+                        } else {
+                            const float2 f = __half22float2(hv);
+                            y2 = __floats2half2_rn(fmaf(f.x, tanh_approx(f.x), f.x), fmaf(f.y, tanh_approx(f.y), f.y));
+                        }
+                        o[k2] = *reinterpret_cast<const uint32_t*>(&y2);
+                    }
+                } else {
+                    const float r2 = __shfl_sync(0xffffffffu, m_r2, i);
+                    const float d0 = __shfl_sync(0xffffffffu, m_d0, i);
 #pragma unroll
                     for (int k2 = 0; k2 < 4; ++k2) {
                         const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ca[k2]), *reinterpret_cast<const __half2*>(&cb[k2]));
                         const float2 f = __half22float2(sum);
-                        y[2 * k2] = silu_half<FMT>(fmaf(d0, wd[2 * k2], fmaf(r2, wr[2 * k2], f.x)));
-                        y[2 * k2 + 1] = silu_half<FMT>(fmaf(d0, wd[2 * k2 + 1], fmaf(r2, wr[2 * k2 + 1], f.y)));
+                        o[k2] = pack2<FMT>(silu_half<SFMT>(fmaf(d0, wd[2 * k2], fmaf(r2, wr[2 * k2], f.x))),
+                                           silu_half<SFMT>(fmaf(d0, wd[2 * k2 + 1], fmaf(r2, wr[2 * k2 + 1], f.y))));
                     }
                 }
-                *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) =            // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
-                    make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+                *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) = make_uint4(o[0], o[1], o[2], o[3]);   // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
                 // refill the slot with the same edge of the next tile
                 pb[i] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, n_col, i), ldp_b));
             }
@@ -326,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             if (lane == 0) mbar_arrive(smem_u32(&s.bar_tempty[ts]));
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { v0[j] = silu_half<FMT>(fmaf(0.5f, v0[j], hb0)); v1[j] = silu_half<FMT>(fmaf(0.5f, v1[j], hb1)); }
+            for (int j = 0; j < 16; ++j) { v0[j] = silu_half<SFMT>(fmaf(0.5f, v0[j], hb0)); v1[j] = silu_half<SFMT>(fmaf(0.5f, v1[j], hb1)); }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 3);
             float gate = 1.f;
             if (gated) {
@@ -405,15 +450,30 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 
 }  // namespace
 
+template <int MODE>
+static int edge_set_smem(int smem)
+{
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return DP_OK;
+}
+
 int tc_edge_init()
 {
     static_assert(sizeof(EdgeSmem) + 1024 <= 232448, "edge kernel shared memory exceeds 227 KB");
     const int smem = (int)sizeof(EdgeSmem) + 1024;
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<tc::FMT_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    return DP_OK;
+    int rc = edge_set_smem<tc::MODE_F16>(smem);
+    if (!rc) rc = edge_set_smem<tc::MODE_BF16>(smem);
+    if (!rc) rc = edge_set_smem<tc::MODE_F16P>(smem);
+    if (!rc) rc = edge_set_smem<tc::MODE_F16Q>(smem);
+    return rc;
+}
+
+template <int MODE>
+static cudaError_t edge_launch(dp_handle* h, const EdgeArgs& a, const unsigned char* img, int grid, int smem, cudaStream_t st)
+{
+    if (a.trace) return launch_kernel(h->pdl, edge_tc_kernel<MODE, true>, dim3(grid), dim3(THREADS), smem, st, a, img);
+    return launch_kernel(h->pdl, edge_tc_kernel<MODE, false>, dim3(grid), dim3(THREADS), smem, st, a, img);
 }
 
 int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
@@ -429,12 +489,12 @@ int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
     const int smem = (int)sizeof(EdgeSmem) + 1024;
     const int grid = h->sm_count;
     const unsigned char* img = L.img[fmt];
-    if (a.trace) {
-        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16, true>, dim3(grid), dim3(THREADS), smem, st, a, img));
-        else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16, true>, dim3(grid), dim3(THREADS), smem, st, a, img));
-    } else {
-        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_BF16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
-        else DP_CUDA(launch_kernel(h->pdl, edge_tc_kernel<tc::FMT_F16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    switch (h->precision) {
+    case DP_BF16: DP_CUDA(edge_launch<tc::MODE_BF16>(h, a, img, grid, smem, st)); break;
+    case DP_F16: DP_CUDA(edge_launch<tc::MODE_F16>(h, a, img, grid, smem, st)); break;
+    case DP_F16_FAST: DP_CUDA(edge_launch<tc::MODE_F16P>(h, a, img, grid, smem, st)); break;
+    case DP_F16_FAST32: DP_CUDA(edge_launch<tc::MODE_F16Q>(h, a, img, grid, smem, st)); break;
+    default: DP_CHECK(false, DP_ERR_STATE, "precision %d has no tcgen05 edge kernel", h->precision);
     }
     h->launches += 1;
     DP_CUDA(cudaGetLastError());

@@ -111,7 +111,7 @@ int tc_prepare_weights(dp_handle* h)
 int tc_fmt_of(dp_handle* h, int* fmt)
 {
     if (h->precision == DP_BF16) { *fmt = FMT_BF16; return DP_OK; }
-    if (h->precision == DP_F16) { *fmt = FMT_F16; return DP_OK; }
+    if (h->precision == DP_F16 || h->precision == DP_F16_FAST || h->precision == DP_F16_FAST32) { *fmt = FMT_F16; return DP_OK; }
     dp_set_error("precision mode %d: the tcgen05 kind::tf32 path (streamed fp32 weight tiles) is not built yet; "
                  "use DP_FP32, DP_F16 (same 10-bit mantissa as TF32) or DP_BF16", h->precision);
     return DP_ERR_INVALID;

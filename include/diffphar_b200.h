@@ -37,7 +37,10 @@ typedef enum dp_precision {
     DP_FP32 = 0,            /* CUDA-core FFMA contractions (reference-grade numerics) */
     DP_TF32 = 1,            /* tcgen05 kind::tf32 tiles, fp32 accumulate in TMEM */
     DP_BF16 = 2,            /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate */
-    DP_F16 = 3              /* tcgen05 kind::f16 (fp16 operands), fp32 accumulate */
+    DP_F16 = 3,             /* tcgen05 kind::f16 (fp16 operands), fp32 accumulate; accurate SiLU (ex2 / rcp) */
+    DP_F16_FAST = 4,        /* fp16 operands; the edge kernels' first layer runs in packed f16x2 (two channels per
+                               instruction) and SiLU takes the one-MUFU tanh form: the throughput mode */
+    DP_F16_FAST32 = 5       /* as DP_F16_FAST with the first layer's tanh in fp32 (A/B of the f16 MUFU rate) */
 } dp_precision;
 
 /* Architecture of EGNNDynamics (ctor: equivariant_diffusion/dynamics.py:10-73,

@@ -30,7 +30,7 @@ for name in ["ca_small", "fa_small", "nocut", "mean_agg"]:
     g = load(f"dynamics_{name}.npz")
     cfg = case_config(name)
     B = len(g["sizes"])
-    for prec in ("f16", "bf16"):
+    for prec in ("f16", "f16fast", "f16fast32", "bf16"):
         h = handle(cfg, int(g["wseed"]), prec)
         h.plan(g["counts"], g["sizes"])
         worst_h, worst_x = 0.0, 0.0
@@ -41,7 +41,7 @@ for name in ["ca_small", "fa_small", "nocut", "mean_agg"]:
             worst_h = max(worst_h, np.abs(out_p[:, 3:] - rp[:, 3:]).max() / max(1.0, np.abs(rp[:, 3:]).max()),
                           np.abs(out_r[:, 3:] - rr[:, 3:]).max() / max(1.0, np.abs(rr[:, 3:]).max()))
             worst_x = max(worst_x, np.abs(out_p[:, :3] - rp[:, :3]).max() / max(1e-12, np.abs(rp[:, :3]).max()))
-        print(f"  {name:9s} {prec:5s} features {worst_h:.2e}   velocity (rel. to max|vel|) {worst_x:.2e}")
+        print(f"  {name:9s} {prec:9s} features {worst_h:.2e}   velocity (rel. to max|vel|) {worst_x:.2e}")
 
 cfg = DynamicsConfig()
 B, n_res, n_ph = 64, 150, 8
@@ -52,15 +52,15 @@ z = torch.cat([com + 5.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(
 xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
 t = torch.full((B,), 0.4)
 outs = {}
-for prec in ("fp32", "f16", "bf16"):
+for prec in ("fp32", "f16", "f16fast", "f16fast32", "bf16"):
     h = handle(cfg, 0, prec)
     h.plan([n_ph] * B, [n_res] * B)
     a, r = h.dynamics_forward(z, xr, t)
     outs[prec] = (a.cpu(), r.cpu())
-for prec in ("f16", "bf16"):
+for prec in ("f16", "f16fast", "f16fast32", "bf16"):
     a, r = outs[prec]
     rp, rr = outs["fp32"]
-    print(f"  config2   {prec:5s} features {float(max((a[:, 3:] - rp[:, 3:]).abs().max() / max(1.0, float(rp[:, 3:].abs().max())), (r[:, 3:] - rr[:, 3:]).abs().max() / max(1.0, float(rr[:, 3:].abs().max())))):.2e}"
+    print(f"  config2   {prec:9s} features {float(max((a[:, 3:] - rp[:, 3:]).abs().max() / max(1.0, float(rp[:, 3:].abs().max())), (r[:, 3:] - rr[:, 3:]).abs().max() / max(1.0, float(rr[:, 3:].abs().max())))):.2e}"
           f"   velocity {float((a[:, :3] - rp[:, :3]).abs().max() / rp[:, :3].abs().max()):.2e}")
 
 print("== K1 radius graph: scan vs cell list (CUDA events, 20 builds)")

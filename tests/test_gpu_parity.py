@@ -154,10 +154,12 @@ def test_dynamics_fp32_vs_reference(name):
 
 
 # tensor-core modes: fp16 operands carry TF32's 10-bit mantissa, bf16 8 bits -> tighter bound for f16
-TC_TOL = {"f16": (1e-4, 0.02), "bf16": (1e-3, 0.05)}
+# "f16fast" = f16 operands with the edge kernels' first layer in packed f16x2 and tanh-form SiLU: between the two
+TC_TOL = {"f16": (1e-4, 0.02), "f16fast": (4e-4, 0.04), "bf16": (1e-3, 0.05)}
+TC_MODES = ("f16", "f16fast", "bf16")
 
 
-@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("prec", list(TC_MODES))
 @pytest.mark.parametrize("name", CASES)
 def test_dynamics_tensor_core_modes_vs_reference(name, prec):
     g = load(f"dynamics_{name}.npz")
@@ -188,13 +190,13 @@ def test_tensor_core_modes_at_full_size_agree_with_fp32():
     xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
     t = torch.full((B,), 0.4)
     outs = {}
-    for prec in ("fp32", "f16", "bf16"):
+    for prec in ("fp32",) + TC_MODES:
         h = make_handle(cfg, 0, prec)
         h.plan([n_ph] * B, [n_res] * B)
         a, r = h.dynamics_forward(z, xr, t)
         outs[prec] = (a.cpu(), r.cpu())
     ref_p, ref_r = outs["fp32"]
-    for prec in ("f16", "bf16"):
+    for prec in TC_MODES:
         tol_h, tol_v = TC_TOL[prec]
         a, r = outs[prec]
         assert (a[:, 3:] - ref_p[:, 3:]).abs().max() <= tol_h * max(1.0, float(ref_p[:, 3:].abs().max()))
@@ -217,7 +219,7 @@ def test_large_pocket_configs_tensor_core_vs_fp32(label, n_res, n_ph, B, res_nf,
     xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
     t = torch.full((B,), 0.3)
     outs, edges = {}, {}
-    for prec in ("fp32", "f16", "bf16"):
+    for prec in ("fp32",) + TC_MODES:
         h = make_handle(cfg, 0, prec)
         h.plan([n_ph] * B, [n_res] * B)
         a, r = h.dynamics_forward(z, xr, t)
@@ -225,10 +227,10 @@ def test_large_pocket_configs_tensor_core_vs_fp32(label, n_res, n_ph, B, res_nf,
         assert fl.edge_overflow == 0 and fl.nan_resets == 0
         outs[prec] = (a.cpu(), r.cpu())
         edges[prec] = (fl.last_n_edges, fl.last_n_edges_phar)
-    assert edges["fp32"] == edges["f16"] == edges["bf16"] and edges["fp32"][0] > 40 * B * n_res * 0.5
+    assert edges["fp32"] == edges["f16"] == edges["f16fast"] == edges["bf16"] and edges["fp32"][0] > 40 * B * n_res * 0.5
     ref_p, ref_r = outs["fp32"]
     errs = {}
-    for prec in ("f16", "bf16"):
+    for prec in TC_MODES:
         tol_h, tol_v = TC_TOL[prec]
         a, r = outs[prec]
         eh = float(max((a[:, 3:] - ref_p[:, 3:]).abs().max(), (r[:, 3:] - ref_r[:, 3:]).abs().max()))
@@ -357,7 +359,7 @@ def inject(ddpm, noise):
     ddpm.sample_gaussian = lambda size, device: next(it).to(device)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16", "f16fast", "bf16"])
 @pytest.mark.parametrize("fixture,name", [("sampler_ca_small_T500_n12.npz", "ca_small"),
                                           ("sampler_ca_small_T20.npz", "ca_small"),
                                           ("sampler_fa_small_T500_n6.npz", "fa_small")])
@@ -379,8 +381,9 @@ def test_sample_given_pocket_vs_reference(fixture, name, prec):
     ref_err = np.abs(g["xh_phar_f32"][:, :3] - g["xh_phar_f64"][:, :3]).max()
     err = np.abs(xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]).max()
     # end-to-end bound: fp32 within 10x the reference's own fp32-vs-fp64 error (or 1e-4 of the scale);
-    # f16 operands 3e-4, bf16 1e-3 of the coordinate scale
-    bound = {"fp32": max(10 * ref_err, 1e-4 * scale), "f16": 3e-4 * scale, "bf16": 1e-3 * scale}[prec]
+    # f16 operands 3e-4, packed-f16 fast mode 6e-4, bf16 1e-3 of the coordinate scale
+    bound = {"fp32": max(10 * ref_err, 1e-4 * scale), "f16": 3e-4 * scale, "f16fast": 6e-4 * scale,
+             "bf16": 1e-3 * scale}[prec]
     assert err <= bound, (err, ref_err, scale)
     same = (xh_phar.cpu().numpy()[:, 3:] == g["xh_phar_f32"][:, 3:]).all(1).mean()
     assert same == 1.0 if prec == "fp32" else same >= 0.9          # type agreement
