@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DIFFPHAR_PRECISION", "bf16"),
+    ap.add_argument("--precision", default=os.environ.get("DIFFPHAR_PRECISION", "f16fast"),
                     choices=["fp32", "tf32", "bf16", "f16", "f16fast", "f16fast32"])
     ap.add_argument("--timesteps", type=int, default=WORKLOAD["T"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
     tfile = os.path.join(ROOT, "profiles", "edge_msg_traffic.json")
     if os.path.exists(tfile):
         try:
-            traffic = json.load(open(tfile)).get(args.precision)
+            traffic = json.load(open(tfile)).get(args.workload, {}).get(args.precision)
         except Exception:
             traffic = None
 
@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32"}.get(args.precision, args.precision), "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "f16fast": "f16", "f16fast32": "f16"}.get(args.precision, args.precision), "data": "synthetic",
         "config": {"workload": "%s, T=%d, hidden 256, %d blocks, cutoff 6A (crossdocked_ca_cond.yml), "
                                "random-init weights" % (WORKLOAD["label"], args.timesteps, WORKLOAD["n_layers"]),
                    "nodes": N, "edges_last_step": E, "precision": args.precision,

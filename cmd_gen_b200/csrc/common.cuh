@@ -208,6 +208,7 @@ struct dp_handle {
     int device = 0;
     int sm_count = 148;
     int precision = 0;
+    int early_fill = 0;                // DIFFPHAR_EARLY_FILL: see EdgeArgs::early_fill
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
     int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells
@@ -266,6 +267,7 @@ struct EdgeArgs {
     const int* edst;                                 // per-edge segmented-sum destination (graph.cu), tcgen05 path
     int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
+    int early_fill;                                  // tcgen05 path: weights -> tensor memory ahead of the grid dependency / edge count
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)

@@ -123,6 +123,32 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     const uint32_t tmem_base = tmem_w + W_COLS;              // accumulator stages
     static_assert(W_COLS + N_TS * TS_COLS <= TMEM_COLS, "tensor memory budget");
     pdl_launch_dependents();
+    // Resident weights: thread (q, lane) of epilogue group gi owns row c = 128 (gi & 1) + 32 q + lane of the [out][in]
+    // matrix = TMEM lane 32 q + lane of M-half gi & 1, K panels 2 (gi >> 1) and 2 (gi >> 1) + 1.  The 128 K elements are
+    // read from the swizzled panel image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 64 packed
+    // 32-bit columns.  Launch-invariant data: with a.early_fill the fill runs ahead of the grid dependency and of
+    // the edge count (all 148 CTAs pull the same 128 KB at once: ~19 MB through L2, the largest part of the
+    // pipeline fill), otherwise after them and only in CTAs that have tiles.
+    auto fill_weights = [&]() {
+        const int q = wid & 3, gi = wid >> 2;
+        const int mh = gi & 1, r = 128 * mh + 32 * q + lane;
+#pragma unroll 1
+        for (int kp = 2 * (gi >> 1); kp < 2 * (gi >> 1) + 2; ++kp) {
+            const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
+            uint32_t wa[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
+                wa[4 * c] = t.x; wa[4 * c + 1] = t.y; wa[4 * c + 2] = t.z; wa[4 * c + 3] = t.w;
+            }
+            tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + mh * 128 + kp * 32, wa);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.bar_w));
+    };
+    if (a.early_fill && wid < EPI_WARPS) fill_weights();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     // The producers' first-tile metadata does not wait for the edge count: loaded speculatively (the arrays hold
     // ecap entries) and masked once E has arrived — one L2 round trip less in the pipeline fill
@@ -325,28 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* redw = s.red[ew];
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
-        if (my_tiles > 0) {
-            // resident weights: thread (q, lane) of group gi owns row c = 128 (gi & 1) + 32 q + lane of the [out][in]
-            // matrix = TMEM lane 32 q + lane of M-half gi & 1, K panels 2 (gi >> 1) and 2 (gi >> 1) + 1.  The 128 K
-            // elements are read from the swizzled panel image (chunk c of a row sits at chunk c ^ (row % 8)) and
-            // stored as 64 packed 32-bit columns.  All 16 warps share the fill: two dependent L2 round trips.
-            const int mh = gi & 1, r = 128 * mh + 32 * q + lane;
-#pragma unroll 1
-            for (int kp = 2 * (gi >> 1); kp < 2 * (gi >> 1) + 2; ++kp) {
-                const unsigned char* src = w_img + (size_t)kp * W_PANEL_BYTES + (size_t)r * 128;
-                uint32_t wa[32];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 t = *reinterpret_cast<const uint4*>(src + ((c ^ (r & 7)) << 4));
-                    wa[4 * c] = t.x; wa[4 * c + 1] = t.y; wa[4 * c + 2] = t.z; wa[4 * c + 3] = t.w;
-                }
-                tmem_st32(tmem_w + ((uint32_t)(32 * q) << 16) + mh * 128 + kp * 32, wa);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s.bar_w));
-        }
+        if (!a.early_fill && my_tiles > 0) fill_weights();
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
             const int tile = blockIdx.x + it * gridDim.x;

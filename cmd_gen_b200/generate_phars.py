@@ -34,7 +34,7 @@ def build_parser():
     parser.add_argument('--resamplings', type=int, default=10)
     parser.add_argument('--jump_length', type=int, default=1)
     parser.add_argument('--timesteps', type=int, default=None)
-    parser.add_argument('--precision', type=str, default='bf16', choices=['fp32', 'bf16', 'f16', 'f16fast'])
+    parser.add_argument('--precision', type=str, default='f16fast', choices=['fp32', 'bf16', 'f16', 'f16fast'])
     return parser
 
 

@@ -36,7 +36,7 @@ class PharPocketDDPM(torch.nn.Module):
     def __init__(self, outdir=None, dataset="crossdock", datadir=None, batch_size=1, lr=0.0, egnn_params=None,
                  diffusion_params=None, num_workers=0, augment_noise=0, augment_rotation=False, clip_grad=False,
                  eval_epochs=0, eval_params=None, mode="pocket_conditioning", node_histogram=None,
-                 pocket_representation="CA", precision="bf16"):
+                 pocket_representation="CA", precision="f16fast"):
         super().__init__()
         if mode != "pocket_conditioning":
             raise NotImplementedError(f"mode '{mode}': only 'pocket_conditioning' (ConditionalDDPM) is on the "
