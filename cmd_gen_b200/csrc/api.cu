@@ -113,6 +113,8 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     }
     if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
     if (const char* m = getenv("DIFFPHAR_EARLY_FILL")) h->early_fill = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {

@@ -208,6 +208,8 @@ struct dp_handle {
     int device = 0;
     int sm_count = 148;
     int precision = 0;
+    int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
+    int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
     int early_fill = 0;                // DIFFPHAR_EARLY_FILL: see EdgeArgs::early_fill
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm

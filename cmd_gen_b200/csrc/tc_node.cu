@@ -58,6 +58,8 @@ struct NodeArgs {
     int row_block; int n_moving;                 // block `row_block` (row part Qa of the coordinate MLP, -1: none) is only read for rows < n_moving
                                                  // (update_coords_mask keeps phar rows, dynamics.py:105-107): tiles past them skip it
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
+    int dbg;                                     // timing experiments (DIFFPHAR_DBG), 0 in production
+    int fast_silu;                               // SiLU in the one-MUFU tanh form (DP_F16_FAST / DP_F16_FAST32; bf16 always uses it)
 };
 
 // debug timeline of CTA 0: role 0 = compute warp 0, 1 = MMA thread, 2 = TMA thread; 16 slots per (role, row)
@@ -311,7 +313,16 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 float v[16];
                 tmem_ld16(tmem_base + t_lane + half * NT + i0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) store_k16<FMT>(s.xa, i0 + j, ch, silu_tc<FMT>(v[j] + b3c));
+                for (int j = 0; j < 16; ++j) v[j] += b3c;
+                if (a.fast_silu) {                                                   // one-MUFU tanh form (DP_F16_FAST): epilogue 1 is MUFU-bound
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = silu_tc<FMT_BF16>(v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = silu_tc<FMT>(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) store_k16<FMT>(s.xa, i0 + j, ch, v[j]);
             }
             release_acc(0);
             publish(1);
@@ -379,6 +390,322 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
     if (wid == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ====================================================================================================
+// CTA-pair version: a cluster of two CTAs (one TPC) runs each GEMM as tcgen05.mma.cta_group::2 —
+// M = 256 output channels split 128 / 128 across the two SMs, N = the nodes of BOTH CTAs.  Each CTA
+// streams only ITS half of every weight panel (16 KB instead of 32 KB): the per-SM weight traffic — the
+// single-CTA kernel's bound (every CTA pulls all 640-896 KB through L2 -> SM delivery) — is halved.
+// CTA r's tensor memory holds channels 128 r .. 128 r + 127 for all nodes of the pair, so its epilogue
+// produces K panels 2 r and 2 r + 1 of the next GEMM's B tile of BOTH CTAs: the own half goes straight into
+// the own tile, the peer's half into a staging buffer that ONE bulk copy (cp.async.bulk shared::cta ->
+// shared::cluster, async proxy on both ends, complete_tx on the peer's mbarrier) ships across — remote
+// 16-bit generic stores measured 2 k cycles slower per epilogue and need a GPU-scope membar.
+//   * leader (cluster rank 0) MMA warp issues every MMA and commits with .multicast::cluster to the
+//     mbarriers of both CTAs; the peer's MMA warp forwards "my half of panel p / my received half tile has
+//     landed" to the leader in the order the leader consumes them;
+//   * tile-ready and accumulator-drained barriers live in the leader and count the compute warps of both
+//     CTAs (relaxed remote arrive after a CTA-scope fence.proxy.async: every CTA only writes its OWN memory).
+// ====================================================================================================
+constexpr int N_WS2 = 6;                          // ring slots of half panels
+constexpr int W_HALF_BYTES = W_PANEL_BYTES / 2;   // 16 KB: 128 channels x 64 K
+
+struct NodeSmem2 {
+    unsigned char xa[X_BYTES];
+    unsigned char xb[X_BYTES];
+    unsigned char stg[2 * NX_PANEL];              // this CTA's two K panels of the PEER's next B tile, before the bulk copy
+    unsigned char w[N_WS2][W_HALF_BYTES];         // 96 KB ring
+    unsigned long long bar_wfull[N_WS2], bar_wempty[N_WS2], bar_wpeer[N_WS2];
+    unsigned long long bar_x[4];                  // used in the leader: agg, t, new h, h tiles (own parts) of BOTH CTAs written
+    unsigned long long bar_stage[2];              // per CTA: staging buffer complete (t, new h) -> warp 0 ships it
+    unsigned long long bar_rx[2];                 // per CTA: the peer's half of my t / new-h tile has landed (complete_tx)
+    unsigned long long bar_rxpeer[2];             // used in the leader: the peer received ITS half
+    unsigned long long bar_accfull[2];            // per CTA (multicast commit)
+    unsigned long long bar_accempty[2];           // used in the leader: both CTAs drained the accumulator
+    uint32_t tmem_holder;
+};
+
+// 4 MMAs of one K panel: D[256 x N] (+)= [W half of rank 0 ; W half of rank 1][256 x 64] * [X rank 0 ; X rank 1][N x 64]^T
+__device__ __forceinline__ void issue_panel_pair(uint32_t tmem_d, uint32_t w_slot, uint32_t x_panel, uint32_t idesc, bool first)
+{
+#pragma unroll
+    for (int ks = 0; ks < PANEL_K / 16; ++ks)
+        umma_f16_pair(tmem_d, make_desc(w_slot + ks * 32), make_desc(x_panel + ks * 32), idesc, (!first || ks > 0) ? 1u : 0u);
+}
+
+template <int FMT>
+__device__ __forceinline__ unsigned short bits16(float v)
+{
+    if (FMT == FMT_BF16) { const __nv_bfloat16 t = __float2bfloat16_rn(v); return *reinterpret_cast<const unsigned short*>(&t); }
+    const __half t = __float2half_rn(v);
+    return *reinterpret_cast<const unsigned short*>(&t);
+}
+
+template <int FMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pair_kernel(NodeArgs a, const unsigned char* __restrict__ w_img)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // same offset in both CTAs
+    NodeSmem2& s = *reinterpret_cast<NodeSmem2*>(base);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const int n0_pair = (int)(blockIdx.x & ~1u) * a.stride;                  // first node of rank 0
+    const int n0 = n0_pair + (int)rank * a.stride;                           // first node of this CTA
+    const int skip_b = (a.row_block >= 0 && n0_pair >= a.n_moving) ? a.row_block : -1;   // pair-uniform
+    const int mlp_panels = a.do_mlp ? 12 : 0;
+    const int nm = a.n_mma;                                                  // B rows per CTA (multiple of 16); the MMA's N = 2 nm
+    const uint32_t ship_bytes = (uint32_t)(NX_PANEL + nm * 128);             // panel 0 whole + rows < nm of panel 1 (rows >= nm are never read)
+
+    if (tid == 0) {
+        for (int i = 0; i < N_WS2; ++i) {
+            mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), 1); mbar_init(smem_u32(&s.bar_wpeer[i]), 1);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.bar_x[i]), 2 * COMPUTE_WARPS);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&s.bar_stage[i]), COMPUTE_WARPS); mbar_init(smem_u32(&s.bar_rx[i]), 1); mbar_init(smem_u32(&s.bar_rxpeer[i]), 1);
+            mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), 2 * COMPUTE_WARPS);
+        }
+        fence_barrier_init();
+        if (a.do_mlp) { mbar_expect_tx(smem_u32(&s.bar_rx[0]), ship_bytes); mbar_expect_tx(smem_u32(&s.bar_rx[1]), ship_bytes); }
+    }
+    if (wid == MMA_WARP) tmem_alloc_pair(smem_u32(&s.tmem_holder), 512);     // the same warp of both CTAs
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                      // the peer's barriers exist (and are armed) before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_holder;
+    pdl_launch_dependents();
+
+    if (wid == TMA_WARP) {
+        // ================================ weight stream: this CTA's 128 channels of every panel ================================
+        const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
+        int p = 0;
+        for (int g = 0; g < mlp_panels + 4 * a.n_blocks; ++g) {
+            if (g >= mlp_panels && (g - mlp_panels) / 4 == skip_b) continue;
+            const int slot = p % N_WS2;
+            if (lane == 0) trace_mark(a.trace, 2, p, 0);
+            mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS2) & 1) ^ 1);
+            if (lane == 0) trace_mark(a.trace, 2, p, 1);
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_HALF_BYTES);
+                bulk_g2s(w0 + slot * W_HALF_BYTES, w_img + (size_t)g * W_PANEL_BYTES + (size_t)rank * W_HALF_BYTES, W_HALF_BYTES,
+                         smem_u32(&s.bar_wfull[slot]));
+            }
+            __syncwarp();
+            ++p;
+        }
+    } else if (wid == MMA_WARP) {
+        const int n_proj = a.n_blocks - (skip_b >= 0 ? 1 : 0);
+        if (rank == 0) {
+            // ================================ MMA issuer (leader) ================================
+            const uint32_t idesc = make_idesc(FMT, 256, 2 * nm);
+            const uint32_t td = warp_uniform(tmem_base);
+            const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
+            const uint32_t xa = warp_uniform(smem_u32(s.xa)), xb = warp_uniform(smem_u32(s.xb));
+            int p = 0;
+            int acc_uses[2] = {0, 0};
+            // tile `which` of both CTAs is complete: own parts written (32 warps) and, for the exchanged tiles
+            // (t = 1, new h = 2 after the MLP), both shipped halves landed
+            auto wait_tile = [&](int which, int rx) {
+                mbar_wait(smem_u32(&s.bar_x[which]), 0);
+                if (rx >= 0) { mbar_wait(smem_u32(&s.bar_rx[rx]), 0); mbar_wait(smem_u32(&s.bar_rxpeer[rx]), 0); }
+            };
+            auto run_gemm = [&](int acc, uint32_t x0, uint32_t x1, int k_panels) {
+                if (acc_uses[acc] > 0) mbar_wait(smem_u32(&s.bar_accempty[acc]), (acc_uses[acc] - 1) & 1);   // a signal: nothing to acquire
+                tc_fence_after();
+                for (int kp = 0; kp < k_panels; ++kp, ++p) {
+                    const int slot = p % N_WS2;
+                    if (kp == 4) wait_tile(0, -1);
+                    if (lane == 0) trace_mark(a.trace, 1, p, 0);
+                    mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS2) & 1);
+                    mbar_wait(smem_u32(&s.bar_wpeer[slot]), (p / N_WS2) & 1);      // the peer's half arrived through ITS async proxy
+                    tc_fence_after();
+                    if (lane == 0) trace_mark(a.trace, 1, p, 1);
+                    const uint32_t xp = (kp < 4 ? x0 + kp * NX_PANEL : x1 + (kp - 4) * NX_PANEL);
+                    if (elect_one()) {
+                        issue_panel_pair(td + acc * ACC_COLS, w0 + slot * W_HALF_BYTES, xp, idesc, kp == 0);
+                        umma_commit_pair(smem_u32(&s.bar_wempty[slot]), 3);
+                        if (kp == k_panels - 1) umma_commit_pair(smem_u32(&s.bar_accfull[acc]), 3);
+                    }
+                    __syncwarp();
+                    if (lane == 0) trace_mark(a.trace, 1, p, 2);
+                }
+                acc_uses[acc] += 1;
+            };
+            if (a.do_mlp) {
+                wait_tile(3, -1);
+                run_gemm(0, xa, xb, 8);
+                wait_tile(1, 0);
+                run_gemm(1, xa, 0, 4);
+                wait_tile(2, 1);
+            } else {
+                wait_tile(2, -1);
+            }
+            for (int cnt = 0; cnt < n_proj; ++cnt) run_gemm(cnt & 1, xb, 0, 4);
+        } else {
+            // ================================ peer: forwards its arrivals to the leader, in the leader's order ================================
+            const int total = mlp_panels + 4 * n_proj;
+            for (int p = 0; p < total; ++p) {
+                if (a.do_mlp && (p == 8 || p == 12)) {                               // the leader's half of my t / new-h tile
+                    const int rx = p == 8 ? 0 : 1;
+                    mbar_wait(smem_u32(&s.bar_rx[rx]), 0);
+                    if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&s.bar_rxpeer[rx]), 0));
+                    __syncwarp();
+                }
+                const int slot = p % N_WS2;
+                mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS2) & 1);
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&s.bar_wpeer[slot]), 0));
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================================ compute warps ================================
+        // epilogue mapping: warp = (TMEM lane quarter q, chunk phase g); thread = one output channel of this CTA's
+        // half, registers = 16 node columns per tcgen05.ld; the warp takes the 16-column chunks g, g + 4, g + 8 of
+        // the pair's 2 nm columns (columns [0, nm) are rank 0's nodes, [nm, 2 nm) rank 1's)
+        const int q = wid & 3, g = wid >> 2;
+        const int ch = 128 * (int)rank + 32 * q + lane;
+        const uint32_t t_lane = (uint32_t)(32 * q) << 16;
+        const int nv[2] = {max(0, min(a.stride, a.n_rows - n0_pair)), max(0, min(a.stride, a.n_rows - n0_pair - a.stride))};
+        const int n_valid = nv[rank];
+        const int n_chunks = 2 * nm / 16;
+        const uint32_t peer = rank ^ 1u;
+        uint32_t bx[4], bempty[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bx[i] = mapa_u32(smem_u32(&s.bar_x[i]), 0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bempty[i] = mapa_u32(smem_u32(&s.bar_accempty[i]), 0);
+        int acc_uses[2] = {0, 0};
+        auto wait_acc = [&](int acc) {
+            mbar_wait(smem_u32(&s.bar_accfull[acc]), acc_uses[acc] & 1);
+            acc_uses[acc] += 1;
+            tc_fence_after();
+        };
+        auto release_acc = [&](int acc) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(bempty[acc]);         // tcgen05.ld results are in registers (wait::ld): a pure signal
+        };
+        // this warp's share of tile `which` (and of the staging buffer `stage`, -1: none) is written: CTA-scope proxy
+        // fence (every CTA writes only its own shared memory), then plain signals; warp 0 ships the staging buffer
+        auto publish = [&](int which, int stage, unsigned char* peer_tile) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster_relaxed(bx[which]);
+                if (stage >= 0) mbar_arrive(smem_u32(&s.bar_stage[stage]));
+            }
+            if (stage >= 0 && wid == 0) {
+                mbar_wait(smem_u32(&s.bar_stage[stage]), 0);
+                if (elect_one())
+                    bulk_s2peer(mapa_u32(smem_u32(peer_tile) + 2 * rank * NX_PANEL, peer), smem_u32(s.stg), ship_bytes,
+                                mapa_u32(smem_u32(&s.bar_rx[stage]), peer));
+                __syncwarp();
+            }
+        };
+        // 16-bit element (node row i of CTA `owner`, K = ch) of the next B tile: own tile, or the staging copy of the
+        // peer's K panels 2 rank, 2 rank + 1 (same swizzle: 16 rank chunks = 0 mod 8)
+        auto store_tile = [&](unsigned char* local_tile, int owner, int i, float v) {
+            unsigned char* dst = owner == (int)rank ? local_tile + chunk_offset(i, ch >> 3, NX_PANEL)
+                                                    : s.stg + chunk_offset(i, (ch >> 3) - 16 * (int)rank, NX_PANEL);
+            *reinterpret_cast<unsigned short*>(dst + ((ch & 7) << 1)) = bits16<FMT>(v);
+        };
+        const bool tr = wid == 0 && lane == 0;
+        pdl_wait();
+        if (tr) trace_mark(a.trace, 0, 0, 0);
+        if (a.do_mlp) {
+            int rp = 0;
+            if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
+            stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
+            publish(3, -1, nullptr);
+            if (tr) trace_mark(a.trace, 0, 0, 1);
+            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp);
+            publish(0, -1, nullptr);
+            if (tr) trace_mark(a.trace, 0, 0, 2);
+            // ---- epilogue 1: t = SiLU(D1 + b3) -> K panels 2 rank, 2 rank + 1 of both xa tiles
+            const float b3c = a.b3[ch];
+            wait_acc(0);
+            if (tr) trace_mark(a.trace, 0, 0, 3);
+#pragma unroll 1
+            for (int c = g; c < n_chunks; c += 4) {
+                const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
+                if (l0 >= nv[owner]) continue;
+                float v[16];
+                tmem_ld16(tmem_base + t_lane + i0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += b3c;
+                if (a.fast_silu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = silu_tc<FMT_BF16>(v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = silu_tc<FMT>(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) store_tile(s.xa, owner, l0 + j, v[j]);
+            }
+            release_acc(0);
+            publish(1, 0, s.xa);
+            if (tr) trace_mark(a.trace, 0, 0, 4);
+            // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> both xb tiles.  The staging
+            // buffer is free again: acc 1 is full only after GEMM 2 consumed the t tiles, i.e. after the t shipment landed.
+            const float b4c = a.b4[ch];
+            wait_acc(1);
+            if (tr) trace_mark(a.trace, 0, 0, 5);
+#pragma unroll 1
+            for (int c = g; c < n_chunks; c += 4) {
+                const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
+                const int nvo = nv[owner];
+                if (l0 >= nvo) continue;
+                float* hrow = a.h + (size_t)(n0_pair + owner * a.stride + l0) * H + ch;
+                float r[16], v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = (l0 + j < nvo) ? hrow[(size_t)j * H] : 0.f;
+                tmem_ld16(tmem_base + ACC_COLS + t_lane + i0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float o = r[j] + (v[j] + b4c);
+                    if (l0 + j < nvo) hrow[(size_t)j * H] = o;
+                    store_tile(s.xb, owner, l0 + j, (l0 + j < nvo) ? o : 0.f);
+                }
+            }
+            release_acc(1);
+            publish(2, 1, s.xb);
+            if (tr) trace_mark(a.trace, 0, 0, 6);
+        } else {
+            stage_h<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane);
+            publish(2, -1, nullptr);
+        }
+        // ---- epilogue 3: projection blocks -> P (f16)
+        for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
+            if (b == skip_b) continue;
+            const int acc = cnt & 1;
+            ++cnt;
+            const float bias = a.bp[b * 256 + ch];
+            wait_acc(acc);
+            if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
+#pragma unroll 1
+            for (int c = g; c < n_chunks; c += 4) {
+                const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
+                const int nvo = nv[owner];
+                if (l0 >= nvo) continue;
+                float v[16];
+                tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + i0, v);
+                __half* d = a.pq + (size_t)(n0_pair + owner * a.stride + l0) * a.ldp + (size_t)b * 256 + ch;
+#pragma unroll
+                for (int j = 0; j < 16; ++j, d += a.ldp)
+                    if (l0 + j < nvo) *d = __float2half_rn(v[j] + bias);
+            }
+            release_acc(acc);
+            if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                                      // nobody leaves while the peer may still touch its shared / tensor memory
+    if (wid == MMA_WARP) tmem_dealloc_pair(tmem_base, 512);
+}
+
 }  // namespace
 
 int tc_node_init()
@@ -386,6 +713,9 @@ int tc_node_init()
     static_assert(sizeof(NodeSmem) + 1024 <= 232448, "node kernel shared memory exceeds 227 KB");
     DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
     DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    static_assert(sizeof(NodeSmem2) + 1024 <= 232448, "pair node kernel shared memory exceeds 227 KB");
+    DP_CUDA(cudaFuncSetAttribute(node_pair_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem2) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_pair_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem2) + 1024));
     return DP_OK;
 }
 
@@ -405,6 +735,8 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     a.bp = ps.b_half; a.pq = reinterpret_cast<__half*>(p.pq); a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
     a.row_block = ps.off_coord >= 0 ? ps.off_coord / 256 : -1; a.n_moving = p.Np;
     a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
+    a.dbg = h->dbg;
+    a.fast_silu = (h->precision == DP_F16_FAST || h->precision == DP_F16_FAST32) ? 1 : 0;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;
     // whole waves of SMs: the fewest waves that fit NT-node tiles, then the smallest stride that keeps that count
@@ -413,8 +745,17 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     if (stride < 16) stride = 16;
     a.stride = stride; a.n_mma = (stride + 15) / 16 * 16;
     const int grid = (p.N + stride - 1) / stride;
-    const int smem = (int)sizeof(NodeSmem) + 1024;
     const unsigned char* img = h->tc->node[v].img[fmt];
+    if (h->node_pair) {
+        // cluster of two CTAs per pair of tiles (cta_group::2): an odd tile count gets one empty tile
+        const int grid2 = (grid + 1) & ~1, smem2 = (int)sizeof(NodeSmem2) + 1024;
+        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_pair_kernel<tc::FMT_BF16>, dim3(grid2), dim3(THREADS), smem2, st, a, img));
+        else DP_CUDA(launch_kernel(h->pdl, node_pair_kernel<tc::FMT_F16>, dim3(grid2), dim3(THREADS), smem2, st, a, img));
+        h->launches += 1;
+        DP_CUDA(cudaGetLastError());
+        return DP_OK;
+    }
+    const int smem = (int)sizeof(NodeSmem) + 1024;
     if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
     else DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_F16>, dim3(grid), dim3(THREADS), smem, st, a, img));
     h->launches += 1;
