@@ -48,11 +48,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("DIFFPHAR_LIB", LIB_PATH)      # A/B of two builds on one box (scripts/gpu_env_ab.sh)
+    if not os.path.exists(path):
         raise DiffPharError(
-            f"{LIB_PATH} is missing: build it with `python -m cmd_gen_b200.build` "
+            f"{path} is missing: build it with `python -m cmd_gen_b200.build` "
             "(there is no CPU or PyTorch fallback for this path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.dp_last_error.restype = C.c_char_p
     lib.dp_abi_version.restype = C.c_int

@@ -112,6 +112,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
         h->tc_mask = atoi(m) ? 3 : 0;
     }
     if (const char* m = getenv("DIFFPHAR_PDL")) h->pdl = atoi(m) != 0;
+    if (const char* m = getenv("DIFFPHAR_SEG")) h->seg_mode = !strcmp(m, "units") ? 1 : !strcmp(m, "lanes") ? 2 : 0;   // tests force a scheme
     if (const char* m = getenv("DIFFPHAR_EARLY_FILL")) h->early_fill = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
@@ -364,7 +365,16 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
         ecap = (int64_t)((c.edge_cutoff < 0.f || pairs < guess) ? pairs : guess);
     }
     DP_CHECK(ecap < (int64_t)2147483000, DP_ERR_INVALID, "edge capacity %lld exceeds int32 indexing", (long long)ecap);
-    DP_CHECK((int64_t)p.N + 2 * (ecap / UNIT_TC + 2) < (int64_t)2147483000, DP_ERR_INVALID, "batch too large for int32 row indexing");
+    // segmented-sum scheme of the tcgen05 edge kernel (common.cuh): contiguous lanes for full-atom pockets (the same
+    // size criterion as the cell-list graph builder), round-robin tiles with per-unit partial rows for Calpha pockets
+    p.seg_lanes = h->seg_mode == 2 || (h->seg_mode == 0 && p.max_nodes >= 512);
+    p.n_lanes = p.seg_lanes ? 4 * h->sm_count : 0;
+    DP_CHECK(p.n_lanes <= MAX_LANES, DP_ERR_INVALID, "%d SMs: more segmented-sum lanes than agg_src can encode", h->sm_count);
+    DP_CHECK((ecap / UNIT_TC + 2) * (int64_t)(p.seg_lanes ? p.n_lanes : 1) < (int64_t)2147483000, DP_ERR_INVALID,
+             "edge capacity %lld too large for the 32-bit lane arithmetic of the segmented sum", (long long)ecap);
+    DP_CHECK(p.seg_lanes || ecap / UNIT_TC + 2 < (int64_t)(1 << 20), DP_ERR_INVALID,
+             "edge capacity %lld too large for the per-unit segmented-sum scheme (set DIFFPHAR_SEG=lanes)", (long long)ecap);
+    DP_CHECK((int64_t)p.N + 2 * (ecap / UNIT_TC + 2 + MAX_LANES) < (int64_t)2147483000, DP_ERR_INVALID, "batch too large for int32 row indexing");
     p.Ecap = ecap;
     std::vector<int> sample_of(p.N);
     for (int b = 0; b < B; ++b) {
@@ -374,10 +384,13 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     auto& bag = p.allocations;
     int rc = 0;
     const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
-    const size_t units = (size_t)(ecap / UNIT_TC + 2);
+    // partial rows: per 64-edge tile on the FFMA path, per lane on the tcgen05 path (a handful of KB instead of E / 8 KB)
+    size_t units = (size_t)(ecap / UNIT_F32 + 2);
+    if (p.seg_lanes && (size_t)p.n_lanes > units) units = (size_t)p.n_lanes;
+    if (!p.seg_lanes) units = (size_t)(ecap / UNIT_TC + 2);
 #define ALLOC(ptr, count) if ((rc = dev_alloc(bag, &(ptr), (size_t)(count)))) return rc
     ALLOC(p.phar_off, B + 1); ALLOC(p.res_off, B + 1); ALLOC(p.sample_of, p.N);
-    ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1);
+    ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1); ALLOC(p.agg_src, p.N);
     ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.edst, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
     ALLOC(p.counts, 4);
     // bucketed cell list: pays off once a sample has more nodes than a handful of warp sweeps (full-atom pockets)
@@ -516,6 +529,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     };
     AggView av{};
     av.agg = p.agg; av.partials = p.partials; av.rowptr = p.rowptr; av.unit = unit;
+    av.src = unit == UNIT_TC ? p.agg_src : nullptr;
     av.norm = c.normalization_factor; av.inv_norm = 1.0f / c.normalization_factor; av.mean = c.aggregation_mean;
 
     const bool fused_node = h->precision != DP_FP32 && (h->tc_mask & 2);
@@ -535,7 +549,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
         e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
-        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.early_fill = h->early_fill;
+        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.early_fill = h->early_fill; e.contig = p.seg_lanes;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
         e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
@@ -561,7 +575,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
             q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
-            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.early_fill = h->early_fill;
+            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.early_fill = h->early_fill; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;

@@ -60,15 +60,40 @@ inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+// ---------------------------------------------------------------------------
+// Segmented sum of the tcgen05 edge kernel: two work splits, one bookkeeping.  An epilogue group (4 warps) reduces one
+// 16-edge unit (UNIT_TC) per tile and keeps the running sum of the current CSR row in registers.
+//   * lanes (Plan::seg_lanes, full-atom pockets, degree ~ 40): the U = ceil(E / 16) units are split into L contiguous,
+//     balanced ranges ("lanes": one per epilogue group of one CTA, L = 4 x CTAs); lane l owns units
+//     [l U / L, (l + 1) U / L) and walks them in order, so the sum carries from tile to tile and a row is stored
+//     ONCE: whole to agg[row] when its edges lie in one lane (all but <= L - 1 rows), else one partial row per lane.
+//   * units (Calpha pockets, degree ~ 7): tile t = 64 consecutive edges goes to CTA t mod CTAs (consecutive edges
+//     share their Pa rows in L1: measured 17 % faster than lanes at this degree); a "lane" is then a single unit,
+//     l = u, and a row crossing 16-edge boundaries is stored as one partial row per unit.
+// Partial row 2 l + slot: slot 0 = the row that contains the lane's first edge, slot 1 = the row that starts inside
+// the lane and runs past its end.  U L < 2^31 is checked at plan time: 32-bit arithmetic throughout.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned lane_first_unit(unsigned l, unsigned U, unsigned L) { return l * U / L; }
+__host__ __device__ __forceinline__ unsigned lane_of_unit(unsigned u, unsigned U, unsigned L) { return ((u + 1u) * L - 1u) / U; }
+// agg_src[row] (written by the graph builder's fill pass, read by every consumer of the aggregate):
+//   >= 0      : the whole sum is agg[row]
+//   AGG_EMPTY : the row has no edges
+//   otherwise : -(1 + (((first lane << 10) | extra lanes) << 1 | slot of the first piece)): pieces are
+//               partial[2 lf + slot], then partial[2 l] for l = lf + 1 .. lf + extra, added in that order
+constexpr int AGG_EMPTY = -2147483647 - 1;
+constexpr int MAX_LANES = 1024;              // lanes scheme; the units scheme allows 2^20 units (first-lane field of agg_src)
+__host__ __device__ __forceinline__ int agg_src_split(unsigned lf, unsigned extra, unsigned slot) { return -(int)(1u + ((((lf << 10) | extra) << 1) | slot)); }
+
 // Per-row aggregate assembled from the edge kernel's outputs.  A row whose edge range
 // [s,e) lies inside one segmented-sum unit was stored to agg[]; a row that crosses unit
 // boundaries was stored as per-unit partial sums (slot 0: segment containing the unit's
 // first edge, slot 1: the other boundary segment).  Summed here in unit order — no atomics.
 struct AggView {
     const float* agg;        // [N][H] raw sums of complete rows
-    const float* partials;   // [units][2][H]
+    const float* partials;   // [units][2][H] (FFMA path) or [lanes][2][H] (tcgen05 path)
+    const int* src;          // tcgen05 path: agg_src[N] (see above); null: the FFMA path's per-tile scheme below
     const int* rowptr;       // [N+1]
-    int unit;                // edges per unit
+    int unit;                // FFMA path: edges per unit (= tile)
     float inv_norm;          // 1/normalization_factor ('sum'); unused for 'mean'
     float norm;              // normalization_factor
     int mean;                // aggregation_method == 'mean'
@@ -79,8 +104,20 @@ __device__ __forceinline__ float4 agg_load4(const AggView& a, int row, int c)
     const int s = a.rowptr[row], e = a.rowptr[row + 1];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e > s) {
-        const int uf = s / a.unit, ul = (e - 1) / a.unit;
-        if (uf == ul) {
+        const int uf = a.src ? 0 : s / a.unit, ul = a.src ? 0 : (e - 1) / a.unit;
+        if (a.src) {
+            const int code = a.src[row];
+            if (code >= 0) {
+                v = *reinterpret_cast<const float4*>(a.agg + (size_t)code * H + c);
+            } else if (code != AGG_EMPTY) {
+                const unsigned k = (unsigned)(-(code + 1));
+                const unsigned lf = k >> 11, extra = (k >> 1) & 1023u, slot = k & 1u;
+                for (unsigned i = 0; i <= extra; ++i) {
+                    const float4 p = *reinterpret_cast<const float4*>(a.partials + ((size_t)(lf + i) * 2 + (i == 0 ? slot : 0u)) * H + c);
+                    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+                }
+            }
+        } else if (uf == ul) {
             v = *reinterpret_cast<const float4*>(a.agg + (size_t)row * H + c);
         } else {
             for (int u = uf; u <= ul; ++u) {
@@ -163,7 +200,11 @@ struct Plan {
     int* rowptr = nullptr;       // [N+1]
     int* col = nullptr;          // [Ecap]
     int* erow = nullptr;         // [Ecap]
-    int* edst = nullptr;         // [Ecap] segmented-sum destination per edge for 32-edge units (see graph.cu)
+    int* edst = nullptr;         // [Ecap] tcgen05 path: where the running segmented sum is stored after this edge (-1: keep going)
+    int* agg_src = nullptr;      // [N] tcgen05 path: where a consumer finds the row's aggregate (AggView::src)
+    int n_lanes = 0;             // segmented-sum lanes of the tcgen05 edge kernel = 4 x its CTAs; 0 = per-unit scheme (see seg_lanes)
+    int seg_lanes = 0;           // 1: contiguous lane ranges (high-degree graphs: full-atom pockets); 0: round-robin tiles, per-unit
+                                 // partial rows (Calpha pockets: consecutive edges of a tile share their Pa rows in L1)
     float* d0 = nullptr;         // [Ecap] squared input-frame distances (edge_attr, egnn_new.py:195)
     int* counts = nullptr;       // [4]: E, E_p, overflow, spare
     // cell list of the bucketed radius-graph builder (graph.cu), rebuilt by every denoiser evaluation
@@ -176,7 +217,7 @@ struct Plan {
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
     float* tbuf = nullptr;       // [N][H] node-MLP hidden
     float* agg = nullptr;        // [N][H]
-    float* partials = nullptr;   // [units][2][H]
+    float* partials = nullptr;   // [max(FFMA units, lanes)][2][H]
     float* pq = nullptr;         // [N][1024] fp32 (FFMA mode) or [N][1024] f16 pre-scaled by 1/2 (tcgen05 modes)
     float* x_in = nullptr;       // [N][3]
     float* x_a = nullptr;        // [N][3]
@@ -209,6 +250,7 @@ struct dp_handle {
     int sm_count = 148;
     int precision = 0;
     int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
+    int seg_mode = 0;                  // DIFFPHAR_SEG: 0 automatic, 1 units, 2 lanes (Plan::seg_lanes)
     int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
     int early_fill = 0;                // DIFFPHAR_EARLY_FILL: see EdgeArgs::early_fill
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
@@ -269,6 +311,7 @@ struct EdgeArgs {
     const int* edst;                                 // per-edge segmented-sum destination (graph.cu), tcgen05 path
     int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
+    int contig;                                      // tcgen05 path: 1 = contiguous lane ranges, 0 = round-robin 64-edge tiles (Plan::seg_lanes)
     int early_fill;                                  // tcgen05 path: weights -> tensor memory ahead of the grid dependency / edge count
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)

@@ -25,7 +25,7 @@ struct GraphArgs {
     float cutoff;          // < 0: none
     int* deg;
     const int* rowptr;
-    int* col; int* erow; float* d0; int* edst;
+    int* col; int* erow; float* d0; int* edst; int* agg_src; int n_lanes;
     int* counts;           // [0]=E [1]=E_p [2]=overflow
     long long ecap;
     int* cell_start; int* cell_nodes; float* cell_grid;
@@ -37,17 +37,36 @@ __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Where the tcgen05 edge kernel's epilogue stores the running sum after edge `pos` (32-edge units,
-// UNIT_TC), as a row of the contiguous [agg (N rows) | partials (2 per unit)] buffer: -1 = keep
-// accumulating; the row lies inside one unit -> agg row; the row crosses a unit boundary -> partial row
-// N + 2 unit + slot (slot 0: the segment containing the unit's first edge).
-__device__ __forceinline__ int edge_dst(int n_nodes, int row, long long rs, long long re, long long pos)
+// Segmented-sum bookkeeping of one CSR row [rs, re) for the tcgen05 edge kernel (lanes: common.cuh).  Computed once
+// per row by the fill pass: the lanes of its first and last edge.  A row inside ONE lane (all but <= L - 1 rows)
+// is stored whole after its last edge; a row that crosses lane boundaries is stored as one partial row per lane.
+struct RowSeg { unsigned lf, ll, U, L; int N; };   // L == 0: units scheme (lane = unit)
+__device__ __forceinline__ unsigned seg_lane_of(const RowSeg& r, unsigned u) { return r.L ? lane_of_unit(u, r.U, r.L) : u; }
+__device__ __forceinline__ unsigned seg_lane_first(const RowSeg& r, unsigned l) { return r.L ? lane_first_unit(l, r.U, r.L) : l; }
+__device__ __forceinline__ RowSeg row_seg(int n_nodes, long long rs, long long re, int E, int L)
 {
-    const bool is_end = (pos == re - 1) || ((pos & (UNIT_TC - 1)) == UNIT_TC - 1);
-    if (!is_end) return -1;
-    const long long u0 = pos & ~(long long)(UNIT_TC - 1);
-    if (rs >= u0 && re <= u0 + UNIT_TC) return row;
-    return n_nodes + (int)((pos / UNIT_TC) * 2 + (rs <= u0 ? 0 : 1));
+    RowSeg r;
+    r.U = (unsigned)((E + UNIT_TC - 1) / UNIT_TC); r.L = (unsigned)L; r.N = n_nodes;
+    r.lf = r.ll = 0;
+    if (re > rs) { r.lf = seg_lane_of(r, (unsigned)(rs / UNIT_TC)); r.ll = seg_lane_of(r, (unsigned)((re - 1) / UNIT_TC)); }
+    return r;
+}
+// destination of the running sum after edge `pos` of the row: -1 = keep accumulating, else a row of the
+// contiguous [agg (N rows) | partials (2 per lane)] buffer
+__device__ __forceinline__ int edge_dst(const RowSeg& r, int row, long long rs, long long re, long long pos)
+{
+    if (r.lf == r.ll) return pos == re - 1 ? row : -1;
+    const unsigned l = seg_lane_of(r, (unsigned)(pos / UNIT_TC));
+    const long long lane_start = (long long)seg_lane_first(r, l) * UNIT_TC, lane_end = (long long)seg_lane_first(r, l + 1) * UNIT_TC;
+    if (pos != re - 1 && pos != lane_end - 1) return -1;
+    return r.N + (int)(2u * l + (rs <= lane_start ? 0u : 1u));
+}
+__device__ __forceinline__ int row_agg_src(const RowSeg& r, int row, long long rs, long long re)
+{
+    if (re <= rs) return AGG_EMPTY;
+    if (r.lf == r.ll) return row;
+    const long long first_start = (long long)seg_lane_first(r, r.lf) * UNIT_TC;
+    return agg_src_split(r.lf, r.ll - r.lf, rs <= first_start ? 0u : 1u);
 }
 
 // FILL = false: count neighbours into deg[]; FILL = true: write col/erow/d0 at rowptr[row].
@@ -67,6 +86,11 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
         int found = 0;
         long long base = FILL ? (long long)a.rowptr[row] : 0;
         const long long row_end = FILL ? (long long)a.rowptr[row + 1] : 0;
+        RowSeg seg{};
+        if (FILL) {
+            seg = row_seg(a.N, base, row_end, a.rowptr[a.N], a.n_lanes);
+            if (lane == 0) a.agg_src[row] = row_agg_src(seg, row, base, row_end);
+        }
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
             for (int j0 = lo[part]; j0 < hi[part]; j0 += 32) {
@@ -84,7 +108,7 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
                         a.col[pos] = j;
                         a.erow[pos] = row;
                         a.d0[pos] = d2;
-                        a.edst[pos] = edge_dst(a.N, row, base, row_end, pos);
+                        a.edst[pos] = edge_dst(seg, row, base, row_end, pos);
                     }
                 }
                 found += __popc(m);
@@ -235,6 +259,11 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
         long long base = FILL ? (long long)a.rowptr[row] : 0;
         const long long row_start = base;
         const long long row_end = FILL ? (long long)a.rowptr[row + 1] : 0;
+        RowSeg seg{};
+        if (FILL) {
+            seg = row_seg(a.N, row_start, row_end, a.rowptr[a.N], a.n_lanes);
+            if (lane == 0) a.agg_src[row] = row_agg_src(seg, row, row_start, row_end);
+        }
         int found = 0;
         for (int w0 = 0; w0 < n_words; w0 += 32) {
             const int w = w0 + lane;
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
                         a.col[pos] = j;
                         a.erow[pos] = row;
                         a.d0[pos] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
-                        a.edst[pos] = edge_dst(a.N, row, row_start, row_end, pos);
+                        a.edst[pos] = edge_dst(seg, row, row_start, row_end, pos);
                     }
                     ++pos;
                 }
@@ -343,6 +372,7 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     a.x = x_dev; a.sample_of = p.sample_of; a.phar_off = p.phar_off; a.res_off = p.res_off;
     a.N = p.N; a.Np = p.Np; a.cutoff = h->cfg.edge_cutoff;
     a.deg = p.deg; a.rowptr = p.rowptr; a.col = p.col; a.erow = p.erow; a.d0 = p.d0; a.edst = p.edst;
+    a.agg_src = p.agg_src; a.n_lanes = p.n_lanes;
     a.counts = p.counts; a.ecap = p.Ecap;
     a.cell_start = p.cell_start; a.cell_nodes = p.cell_nodes; a.cell_grid = p.cell_grid;
     const int wpb = 8;

@@ -50,8 +50,17 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // Registers are allocated per SM sub-partition (16384 each, 7 warps per sub-partition here), so the launch
 // gets 72 per thread; setmaxnreg then rebalances.  4 Re + 2 Rp + Rm <= 7 x 72: the CTA pool only holds what
 // its own warps released.
-constexpr int REGS_MMA = 32, REGS_PRODUCER = 104, REGS_EPILOGUE = 64;
-static_assert(4 * REGS_EPILOGUE + 2 * REGS_PRODUCER + REGS_MMA <= 7 * 72, "register pool");
+// The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
+// (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
+constexpr int REGS_MMA = 32;
+#ifndef EDGE_REGS_PACKED_PRODUCER
+#define EDGE_REGS_PACKED_PRODUCER 104
+#define EDGE_REGS_PACKED_EPILOGUE 64
+#endif
+__host__ __device__ constexpr int regs_producer(int mode) { return (mode == MODE_F16P || mode == MODE_F16Q) ? EDGE_REGS_PACKED_PRODUCER : 104; }
+__host__ __device__ constexpr int regs_epilogue(int mode) { return (mode == MODE_F16P || mode == MODE_F16Q) ? EDGE_REGS_PACKED_EPILOGUE : 64; }
+static_assert(4 * regs_epilogue(MODE_F16P) + 2 * regs_producer(MODE_F16P) + REGS_MMA <= 7 * 72, "register pool");
+static_assert(4 * regs_epilogue(MODE_BF16) + 2 * regs_producer(MODE_BF16) + REGS_MMA <= 7 * 72, "register pool");
 constexpr int RED_STRIDE = 20;                    // floats per channel row of the transposed-reduce buffer (16 edges + pad)
 
 struct EdgeSmem {                                 // offsets from a 1024-aligned base
@@ -87,11 +96,14 @@ __device__ __forceinline__ void unpack8(const float4& a, const float4& b, float 
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-// debug timeline: role 0 = producer warp 0, 1 = MMA thread, 2 = epilogue warp 0; CTA 0 only
+// debug timeline: role 0 = producer warp 0, 1 = MMA thread, 2 = epilogue warp 0; one CTA (phar-row lanes: CTA 0; pocket rows: 100)
+#ifndef TRACE_CTA
+#define TRACE_CTA 100
+#endif
 template <bool TRACE>
 __device__ __forceinline__ void trace_mark_t(long long* trace, int role, int it, int slot)
 {
-    if (TRACE) { if (blockIdx.x == 0 && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64(); }
+    if (TRACE) { if (blockIdx.x == TRACE_CTA && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64(); }
 }
 #define trace_mark(tr, role, it, slot) trace_mark_t<TRACE>(tr, role, it, slot)
 
@@ -150,16 +162,29 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     };
     if (a.early_fill && wid < EPI_WARPS) fill_weights();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
-    // The producers' first-tile metadata does not wait for the edge count: loaded speculatively (the arrays hold
-    // ecap entries) and masked once E has arrived — one L2 round trip less in the pipeline fill
+    // Work split (common.cuh, "segmented sum of the tcgen05 edge kernel"):
+    //   a.contig = 0 (Calpha pockets): tile t = 64 consecutive edges, CTA t mod gridDim; the first tile's metadata does
+    //     not wait for the edge count (loaded speculatively: the arrays hold ecap entries; masked once E has arrived);
+    //   a.contig = 1 (full-atom pockets): the U 16-edge units are cut into 4 x gridDim contiguous balanced lanes;
+    //     epilogue group g (and the two producer warps that feed it) walks lane 4 blockIdx + g in order, one unit per
+    //     tile, and the running sum of a CSR row stays in the group's registers from tile to tile.
     int s_row = 0, s_col = 0; float s_d0 = 0.f;
-    if (wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+    if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
     const int E = *a.n_edges;
-    const int n_tiles = (E + TILE - 1) / TILE;
-    const int my_tiles = max(0, (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);   // 0: idle CTA, falls through
+    const unsigned U = (unsigned)((E + UNIT_TC - 1) / UNIT_TC), L = 4u * gridDim.x;
+    // tiles of this CTA.  Lanes: its longest lane; lane lengths are floor(U / L) or ceil(U / L), so ceil(U / L) is exact
+    // for every CTA that has a long lane and one (empty, skipped by has_unit) tile too many for the others — which
+    // finish no later than the CTAs that need it.  Idle CTAs fall through with 0.
+    int my_tiles;
+    if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
+    else my_tiles = max(0, ((E + TILE - 1) / TILE - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+    // group g's unit of tile `it` is unit_base(g) + it * unit_step, and exists while it < unit_count(g)
+    const int unit_step = a.contig ? 1 : 4 * (int)gridDim.x;
+    auto unit_base = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
+    auto unit_count = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
 
     if (wid >= MMA_WARP) {
         // ================================ MMA issuer ================================
@@ -201,8 +226,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         //   * Pa changes once per CSR row run: a warp-uniform branch reloads it; the rows a tile will need are
         //     pulled into L1 one tile ahead (one 32-sector touch per row), so the reload is an L1 hit.
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_producer(MODE)));
         const int pw = wid - EPI_WARPS;
+        const int unit0 = unit_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
+        const int e_off = 8 * (pw & 1) + lane;                                           // its half of the unit's 16 edges
         float wr[8], wd[8];
         unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
         unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
@@ -220,12 +247,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         const __half* pa_base = pq + a.off_a + 8 * lane;
         const __half* pb_base = pq + a.off_b + 8 * lane;
         const __half* pa_touch = pq + a.off_a + 16 * (lane & 15);                        // lanes 0-15 touch the 16 sectors of a 512 B row
-        // Edges past E (last tile only) are processed as edge (0, 0): finite garbage in columns nobody reads.
+        // Slots without an edge (past E, or past the end of a shorter lane) are processed as edge (0, 0): finite garbage in columns nobody reads.
         int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
         auto load_rc = [&](int it, int& r, int& c, float& d0) {
-            const int e = (blockIdx.x + it * gridDim.x) * TILE + 8 * pw + lane;
+            const int e = (unit0 + it * unit_step) * UNIT_TC + e_off;
             r = 0; c = 0; d0 = 0.f;
-            if (it < my_tiles && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
+            if (it < n_units && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
         };
         // L1 prefetch of the distinct rows of a group: one cp.async.ca per row, lane l < 16 pulling sector l of the
         // 512 B row through L1 into a scratch word — no destination register, so nothing ever waits on it
@@ -248,8 +275,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
         };
         int n_row, n_col; float n_d0;
-        {
-            const bool ok = my_tiles > 0 && lane < 8 && (int)blockIdx.x * TILE + 8 * pw + lane < E;   // the speculative loads were real edges
+        if (a.contig) {
+            load_rc(0, m_row, m_col, m_d0);
+        } else {
+            const bool ok = my_tiles > 0 && lane < 8 && unit0 * UNIT_TC + e_off < E;       // the speculative loads were real edges
             m_row = ok ? s_row : 0; m_col = ok ? s_col : 0; m_d0 = ok ? s_d0 : 0.f;
         }
         uint4 pb[8];
@@ -339,7 +368,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ epilogue ================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
+        if (regs_epilogue(MODE) > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));
+        else if (regs_epilogue(MODE) < 72) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));
         const int ew = wid, q = ew & 3, gi = ew >> 2;
         const int c0 = 32 * q + lane, c1 = c0 + 128;                                     // this thread's two channels
         const float hb0 = 0.5f * a.b2[c0], hb1 = 0.5f * a.b2[c1];                        // SiLU(v + b) from hv = v / 2 + b / 2
@@ -352,11 +382,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
         if (!a.early_fill && my_tiles > 0) fill_weights();
+        const int unit0 = unit_base(gi), n_units = unit_count(gi);                      // this group's units
+        float s0 = 0.f, s1 = 0.f;                                                        // running sum of the current CSR row: carried across tiles
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int u0 = tile * TILE + GROUP_EDGES * gi;                               // first edge of this group's unit
-            const int my_dst = (!a.coord && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
+            const int u0 = (unit0 + it * unit_step) * UNIT_TC;                           // first edge of this group's unit
+            const bool has_unit = it < n_units;                                          // shorter lanes idle through the CTA's last tile
+            const int my_dst = (!a.coord && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
             mbar_wait_relaxed(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
@@ -415,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 6);
             if (a.coord) {
-                if (q == 0 && lane < GROUP_EDGES && u0 + lane < E) a.escal[u0 + lane] = gate;
+                if (q == 0 && has_unit && lane < GROUP_EDGES && u0 + lane < E) a.escal[u0 + lane] = gate;
             } else {
                 // segmented sum over the unit's edges: thread = channel pair, registers = edges (two FMA chains)
                 if (gated) {
@@ -423,7 +455,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                     __syncwarp();
                 }
                 const unsigned last_mask = __ballot_sync(0xffffffffu, my_dst >= 0);
-                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
                     float gq[4] = {1.f, 1.f, 1.f, 1.f};

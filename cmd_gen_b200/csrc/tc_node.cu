@@ -111,57 +111,46 @@ __device__ __forceinline__ void stage_h(unsigned char* tile, const NodeArgs& a, 
         *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + u, lane, NX_PANEL)) = pack8<FMT>(f[u][0], f[u][1]);
 }
 
-// Aggregated messages -> tile.  A row whose edges lie inside one 16-edge unit was stored whole (agg[row]);
-// a row that crosses unit boundaries was stored as per-unit partial sums (see AggView / graph.cu edge_dst):
-// the first two sources of 3 rows are fetched together, longer rows (degree > 32) take a loop.
-// unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a reciprocal multiply.
-// `rp` = rowptr[first row of the warp + lane] for lanes 0..6, loaded by the caller ahead of time.
+// Aggregated messages -> tile.  agg_src[row] (graph builder, common.cuh) says where the row's sum is: agg[row] for
+// all but the <= L - 1 rows that cross a segmented-sum lane boundary; those are the sum of one partial row per lane
+// crossed, added in lane order.  unsorted_segment_sum's normalisation (egnn_new.py:283-291) is applied as a
+// reciprocal multiply.  `rp` = rowptr[first row of the warp + lane] for lanes 0..6 and `code` = agg_src[first row +
+// lane] for lanes 0..5, both loaded by the caller ahead of time.
 template <int FMT>
-__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int row_end, int wid, int lane, int rp)
+__device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a, int n0, int row_end, int wid, int lane, int rp, int code)
 {
     const AggView& g = a.aggv;
     const int r0 = n0 + ROWS_PER_WARP * wid;
+    float4 f[ROWS_PER_WARP][2];
+    int cd[ROWS_PER_WARP];
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
-        float4 f[3][2], f2[3][2];
-        int s_[3], e_[3];
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {                                      // all 12 loads of the warp in flight together
+        cd[u] = __shfl_sync(0xffffffffu, code, u);
+        if (r0 + u >= row_end) cd[u] = AGG_EMPTY;
+        f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cd[u] != AGG_EMPTY) {
+            const unsigned k = (unsigned)(-(cd[u] + 1));                               // split rows: first piece = partial row 2 lf + slot
+            const float* src = cd[u] >= 0 ? g.agg + (size_t)cd[u] * H : g.partials + ((size_t)(k >> 11) * 2 + (k & 1u)) * H;
+            f[u][0] = *reinterpret_cast<const float4*>(src + 8 * lane);
+            f[u][1] = *reinterpret_cast<const float4*>(src + 8 * lane + 4);
+        }
+    }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int row = r0 + 3 * hb + u;
-            s_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u);
-            e_[u] = __shfl_sync(0xffffffffu, rp, 3 * hb + u + 1);
-            if (row >= row_end) e_[u] = s_[u];
-            f[u][0] = f[u][1] = f2[u][0] = f2[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e_[u] > s_[u]) {
-                const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
-                const float* src = (uf == ul) ? g.agg + (size_t)row * H
-                                              : g.partials + ((size_t)uf * 2 + (s_[u] <= uf * g.unit ? 0 : 1)) * H;
-                f[u][0] = *reinterpret_cast<const float4*>(src + 8 * lane);
-                f[u][1] = *reinterpret_cast<const float4*>(src + 8 * lane + 4);
-                if (ul > uf) {
-                    const float* src2 = g.partials + ((size_t)(uf + 1) * 2) * H;
-                    f2[u][0] = *reinterpret_cast<const float4*>(src2 + 8 * lane);
-                    f2[u][1] = *reinterpret_cast<const float4*>(src2 + 8 * lane + 4);
-                }
+    for (int u = 0; u < ROWS_PER_WARP; ++u) {
+        float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
+        if (cd[u] < 0 && cd[u] != AGG_EMPTY) {                                         // warp-uniform, rare: the remaining pieces
+            const unsigned k = (unsigned)(-(cd[u] + 1)), lf = k >> 11, extra = (k >> 1) & 1023u;
+            for (unsigned i = 1; i <= extra; ++i) {
+                const float* src = g.partials + ((size_t)(lf + i) * 2) * H + 8 * lane;
+                const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
+                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
             }
         }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            float v[8] = {f[u][0].x + f2[u][0].x, f[u][0].y + f2[u][0].y, f[u][0].z + f2[u][0].z, f[u][0].w + f2[u][0].w,
-                          f[u][1].x + f2[u][1].x, f[u][1].y + f2[u][1].y, f[u][1].z + f2[u][1].z, f[u][1].w + f2[u][1].w};
-            if (e_[u] > s_[u]) {
-                const int uf = s_[u] / g.unit, ul = (e_[u] - 1) / g.unit;
-                for (int un = uf + 2; un <= ul; ++un) {                               // rows spanning 3+ units (degree > 16)
-                    const float* src = g.partials + ((size_t)un * 2) * H + 8 * lane;
-                    const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
-                    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-                }
-            }
-            const float sc = g.mean ? __fdividef(1.0f, (float)max(e_[u] - s_[u], 1)) : g.inv_norm;
-            *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + 3 * hb + u, lane, NX_PANEL)) =
-                make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
-                           pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
-        }
+        const int deg = __shfl_sync(0xffffffffu, rp, u + 1) - __shfl_sync(0xffffffffu, rp, u);
+        const float sc = g.mean ? __fdividef(1.0f, (float)max(deg, 1)) : g.inv_norm;
+        *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + u, lane, NX_PANEL)) =
+            make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
+                       pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
     }
 }
 
@@ -294,10 +283,12 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         if (a.do_mlp) {
             int rp = 0;                                                              // CSR bounds of the warp's rows: issued first
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
+            int code = AGG_EMPTY;                                                    // where each row's aggregate lives
+            if (lane < ROWS_PER_WARP && n0 + ROWS_PER_WARP * wid + lane < a.n_rows) code = a.aggv.src[n0 + ROWS_PER_WARP * wid + lane];
             stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
             publish(3);
             if (tr) trace_mark(a.trace, 0, 0, 1);
-            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp);
+            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp, code);
             publish(0);
             if (tr) trace_mark(a.trace, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> xa (the n0 MMAs have all retired: acc_full follows them)
@@ -616,10 +607,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
         if (a.do_mlp) {
             int rp = 0;
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
+            int code = AGG_EMPTY;                                                    // where each row's aggregate lives
+            if (lane < ROWS_PER_WARP && n0 + ROWS_PER_WARP * wid + lane < a.n_rows) code = a.aggv.src[n0 + ROWS_PER_WARP * wid + lane];
             stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
             publish(3, -1, nullptr);
             if (tr) trace_mark(a.trace, 0, 0, 1);
-            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp);
+            stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp, code);
             publish(0, -1, nullptr);
             if (tr) trace_mark(a.trace, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> K panels 2 rank, 2 rank + 1 of both xa tiles

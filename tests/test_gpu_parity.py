@@ -27,18 +27,22 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None):
-    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH)."""
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None):
+    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH);
+    seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG)."""
     import os
-    old = os.environ.pop("DIFFPHAR_GRAPH", None)
-    if graph:
-        os.environ["DIFFPHAR_GRAPH"] = graph
+    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg}
+    old = {k: os.environ.pop(k, None) for k in forced}
+    for k, v in forced.items():
+        if v:
+            os.environ[k] = v
     try:
         h = _lib.Handle(cfg, DEV, precision)
     finally:
-        os.environ.pop("DIFFPHAR_GRAPH", None)
-        if old is not None:
-            os.environ["DIFFPHAR_GRAPH"] = old
+        for k in forced:
+            os.environ.pop(k, None)
+            if old[k] is not None:
+                os.environ[k] = old[k]
     h.set_weights(pack_blob(cfg, init_weights(cfg, wseed)))
     return h
 
@@ -241,6 +245,43 @@ def test_large_pocket_configs_tensor_core_vs_fp32(label, n_res, n_ph, B, res_nf,
         assert (a[:, :3] - ref_p[:, :3]).abs().max() <= 1e-5 * 80 + 2 * tol_v * float(ref_p[:, :3].abs().max())
         assert torch.all(r[:, :3] == 0)
     assert errs["f16"] < errs["bf16"], errs
+
+
+@pytest.mark.parametrize("seg", ["units", "lanes"])
+@pytest.mark.parametrize("label,sizes,counts,res_nf,density", [
+    ("Calpha-sized ragged batch", [150, 97, 211, 1, 180, 64], [8, 4, 12, 1, 6, 9], 20, 0.0074),
+    ("full-atom-sized ragged batch", [900, 1300, 40], [8, 12, 3], 11, 0.05)])
+def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg):
+    """The two work splits of the tcgen05 edge kernel (round-robin 64-edge tiles with per-unit partial rows / contiguous
+    lane ranges with carried row sums) on the same ragged batches: each against the fp32 FFMA mode, CSR identical."""
+    cfg = DynamicsConfig(residue_nf=res_nf, n_layers=3)
+    pocket = make_pocket_batch(sizes, res_nf, density=density, seed=31)
+    gen = torch.Generator().manual_seed(32)
+    n_ph = sum(counts)
+    mask_p = torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+    com = torch.stack([pocket["x"][pocket["mask"] == b].mean(0) for b in range(len(sizes))])
+    z = torch.cat([com[mask_p] + 4.0 * torch.randn(n_ph, 3, generator=gen), torch.randn(n_ph, 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    t = torch.full((len(sizes),), 0.35)
+    ref = make_handle(cfg, 0, "fp32")
+    ref.plan(counts, sizes)
+    rp, rr = ref.dynamics_forward(z, xr, t)
+    rp, rr = rp.cpu(), rr.cpu()
+    for prec in ("f16", "f16fast"):
+        h = make_handle(cfg, 0, prec, seg=seg)
+        h.plan(counts, sizes)
+        a, r = h.dynamics_forward(z, xr, t)
+        fl, flr = h.flags(), ref.flags()
+        assert fl.edge_overflow == 0 and fl.nan_resets == 0
+        assert (fl.last_n_edges, fl.last_n_edges_phar) == (flr.last_n_edges, flr.last_n_edges_phar)
+        tol_h, tol_v = TC_TOL[prec]
+        a, r = a.cpu(), r.cpu()
+        assert (a[:, 3:] - rp[:, 3:]).abs().max() <= 2 * tol_h * max(1.0, float(rp[:, 3:].abs().max())), (label, seg, prec)
+        assert (r[:, 3:] - rr[:, 3:]).abs().max() <= 2 * tol_h * max(1.0, float(rr[:, 3:].abs().max())), (label, seg, prec)
+        assert (a[:, :3] - rp[:, :3]).abs().max() <= 1e-5 * 80 + tol_v * float(rp[:, :3].abs().max())
+        # same inputs twice: the segmented sum has a fixed order (no atomics) -> bit-identical
+        a2, r2 = h.dynamics_forward(z, xr, t)
+        assert torch.equal(a2.cpu(), a) and torch.equal(r2.cpu(), r)
 
 
 def test_dynamics_module_api_and_kwargs():
