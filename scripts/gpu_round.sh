@@ -4,7 +4,7 @@
 # Outputs land in gpurun_out/<tag>_*; copy the summaries you want judged into profiles/.
 set -u
 TAG=${1:-r01}
-PREC=${2:-bf16}
+PREC=${2:-f16fast}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
@@ -32,7 +32,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   python profiles/summarize_launches.py $OUT/${TAG}_${PREC}_launches.csv > $OUT/${TAG}_${PREC}_launches.summary.txt 2>&1
   cat $OUT/${TAG}_${PREC}_launches.summary.txt | head -20
   # the top kernels, full set
-  for K in ${NCU_KERNELS:-edge_tc_kernel linear_tc_kernel}; do
+  for K in ${NCU_KERNELS:-edge_tc_kernel node_tc_kernel}; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 30 -c 3 \
         -o $OUT/${TAG}_${PREC}_$K -f \
         python bench.py --precision $PREC --steps 1 --warmup 1 --timesteps 8 --no-cpu-baseline > $OUT/${TAG}_ncu_$K.log 2>&1
