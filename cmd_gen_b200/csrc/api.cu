@@ -396,7 +396,11 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     // bucketed cell list: pays off once a sample has more nodes than a handful of warp sweeps (full-atom pockets)
     p.use_cells = c.edge_cutoff > 0.f && p.max_nodes <= CELL_SAMPLE_MAX_NODES &&
                   (h->graph_mode == 2 || (h->graph_mode == 0 && p.max_nodes >= 512));
-    if (p.use_cells) { ALLOC(p.cell_start, (size_t)B * (CELLS_MAX + 1)); ALLOC(p.cell_nodes, p.N); ALLOC(p.cell_grid, (size_t)B * 8); }
+    if (p.use_cells) {
+        ALLOC(p.cell_start, (size_t)B * (CELLS_MAX + 1)); ALLOC(p.cell_nodes, p.N); ALLOC(p.cell_grid, (size_t)B * 8);
+        p.bitmap_words = (p.max_nodes + 31) / 32;
+        ALLOC(p.row_bitmap, (size_t)p.N * p.bitmap_words);     // 8 MB at config 3: the fill pass skips the bucket search
+    }
     ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.h_base, (size_t)p.Nr * H);
     ALLOC(p.agg, ((size_t)p.N + units * 2) * H);          // [agg rows | partial rows] contiguous (graph.cu edge_dst)
     p.partials = p.agg + (size_t)p.N * H;

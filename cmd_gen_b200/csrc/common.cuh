@@ -212,6 +212,8 @@ struct Plan {
     int* cell_start = nullptr;   // [B][CELLS_MAX + 1] offsets into cell_nodes (absolute)
     int* cell_nodes = nullptr;   // [N] node ids bucketed by cell, samples back to back
     float* cell_grid = nullptr;  // [B][8]: origin xyz, inverse cell size xyz, dims packed (nx | ny << 8 | nz << 16) as int bits
+    unsigned* row_bitmap = nullptr;  // [N][bitmap_words]: per-row hit bitmap over the sample's nodes, count pass -> fill pass
+    int bitmap_words = 0;        // ceil(max nodes per sample / 32)
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term

@@ -29,6 +29,7 @@ struct GraphArgs {
     int* counts;           // [0]=E [1]=E_p [2]=overflow
     long long ecap;
     int* cell_start; int* cell_nodes; float* cell_grid;
+    unsigned* row_bitmap; int bitmap_words;          // cells builder: the count pass keeps each row's hit bitmap for the fill pass
 };
 
 __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float xj, float yj, float zj)
@@ -227,9 +228,15 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
         const int p0 = a.phar_off[b], np = a.phar_off[b + 1] - p0;
         const int r0 = a.Np + a.res_off[b], nr = a.res_off[b + 1] - a.res_off[b];
         const int n_words = (np + nr + 31) >> 5;
+        const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
+        unsigned* keep = a.row_bitmap ? a.row_bitmap + (size_t)row * a.bitmap_words : nullptr;
+        if (FILL && keep) {
+            // the count pass already searched the 27 buckets: its bitmap comes back from L2 (63 words per row at 2 k nodes)
+            for (int w = lane; w < n_words; w += 32) bm[w] = keep[w];
+            __syncwarp();
+        } else {
         for (int w = lane; w < n_words; w += 32) bm[w] = 0u;
         __syncwarp();
-        const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
         const float* g = a.cell_grid + 8 * b;
         const int dims = __float_as_int(g[6]);
         const int nx = dims & 255, ny = (dims >> 8) & 255, nz = dims >> 16;
@@ -256,6 +263,8 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
             }
         }
         __syncwarp();
+        if (!FILL && keep) for (int w = lane; w < n_words; w += 32) keep[w] = bm[w];
+        }
         long long base = FILL ? (long long)a.rowptr[row] : 0;
         const long long row_start = base;
         const long long row_end = FILL ? (long long)a.rowptr[row + 1] : 0;
@@ -375,6 +384,7 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     a.agg_src = p.agg_src; a.n_lanes = p.n_lanes;
     a.counts = p.counts; a.ecap = p.Ecap;
     a.cell_start = p.cell_start; a.cell_nodes = p.cell_nodes; a.cell_grid = p.cell_grid;
+    a.row_bitmap = p.row_bitmap; a.bitmap_words = p.bitmap_words;
     const int wpb = 8;
     int grid = (p.N + wpb - 1) / wpb;
     const int max_grid = h->sm_count * 16;

@@ -59,6 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 // Wait of a role that is usually early (epilogue / producer warps): the poll loop of 16-24 waiting warps would
 // otherwise eat a seventh of the SM's issue slots; try_wait may suspend up to the hint, then the warp backs off.
+template <int SLEEP_NS = 64>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, P1;\n"
             "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
-        if (!ok) __nanosleep(64);
+        if (!ok) __nanosleep(SLEEP_NS);
     } while (!ok);
 }
 // base + index * stride_bytes in ONE instruction (IMAD.WIDE.U32): gather addresses without 64-bit add chains

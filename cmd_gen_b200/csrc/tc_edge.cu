@@ -34,6 +34,12 @@
 namespace {
 using namespace tc;
 
+#ifndef EDGE_PRODUCER_SLEEP_NS
+#define EDGE_PRODUCER_SLEEP_NS 64
+#endif
+#ifndef EDGE_EPILOGUE_SLEEP_NS
+#define EDGE_EPILOGUE_SLEEP_NS 64
+#endif
 constexpr int TILE = 64;                          // edges per tile (UMMA N)
 constexpr int X_PANEL_BYTES = TILE * 128;         // 8 KB
 constexpr int X_TILE_BYTES = 4 * X_PANEL_BYTES;   // 32 KB: 64 edges x 256 K x 2 B
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const float xr0 = a.x[xr_i], xr1 = a.x[xr_i + 1], xr2 = a.x[xr_i + 2];
             const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
             touch_rows(n_row);
-            mbar_wait_relaxed(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);
+            mbar_wait_relaxed<EDGE_PRODUCER_SLEEP_NS>(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);   // up to 3 tiles ahead: a late wake-up costs nothing
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
             unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
             uint32_t m_rd = 0u;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const bool has_unit = it < n_units;                                          // shorter lanes idle through the CTA's last tile
             const int my_dst = (!a.coord && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
-            mbar_wait_relaxed(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
+            mbar_wait_relaxed<EDGE_EPILOGUE_SLEEP_NS>(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 1);
             float v0[16], v1[16];
