@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     unsigned char* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     EdgeSmem& s = *reinterpret_cast<EdgeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == MMA_WARP * 32) trace_mark(a.trace, 1, 62, 0);                              // kernel entry
 
     // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
     if (tid == 0) {
@@ -488,6 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     tc_fence_before();
     __syncthreads();
     if (wid == MMA_WARP) tmem_dealloc(tmem_w, TMEM_COLS);
+    if (tid == MMA_WARP * 32) trace_mark(a.trace, 1, 62, 1);                              // kernel exit
 }
 
 }  // namespace

@@ -42,6 +42,8 @@ names[4] = names[5] = names[3]
 print("E =", h.flags().last_n_edges, " (cycles relative to the first mark, CTA 0)")
 w = tr[1][63]
 print(f"weights: issue {w[0] - t0}  landed {w[1] - t0}")
+k = tr[1][62]
+print(f"kernel entry {k[0] - t0}  exit {k[1] - t0}  (traced CTA)")
 for it in range(10):
     for r, rn in ((0, "producer"), (1, "mma"), (2, "epilogue0"), (3, "epilogue1"), (4, "epilogue2"), (5, "epilogue3")):
         row = tr[r][it]
