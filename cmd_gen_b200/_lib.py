@@ -20,7 +20,7 @@ EXPORTS = [
     "dp_last_error", "dp_abi_version", "dp_device_count", "dp_create", "dp_destroy", "dp_weight_count",
     "dp_set_weights", "dp_set_precision", "dp_plan", "dp_build_edges", "dp_get_graph", "dp_dynamics_forward",
     "dp_ddpm_update", "dp_set_step_table", "dp_sample", "dp_sample_host", "dp_get_flags", "dp_reset_flags",
-    "dp_launch_count", "dp_profile_enable", "dp_profile_read",
+    "dp_launch_count", "dp_profile_enable", "dp_profile_read", "dp_pointcloud_stats",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library():
     lib.dp_launch_count.restype = i64
     lib.dp_profile_enable.argtypes = [vp, i32]
     lib.dp_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.dp_pointcloud_stats.argtypes = [vp, vp, i32, C.POINTER(C.c_double), vp, vp]
     _lib = lib
     return lib
 

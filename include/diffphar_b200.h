@@ -150,6 +150,14 @@ int64_t dp_launch_count(const dp_handle* h);
 int dp_profile_enable(dp_handle* h, int32_t on);
 int dp_profile_read(dp_handle* h, int32_t which, double* total_ms, int64_t* launches);
 
+/* Evaluation statistics of generated point clouds (reference DiffPhar/test.py:165-197: per "molecule" the number of
+ * points, the distance of their centroid to the reference ligand's centroid, the largest pairwise distance).
+ * xyz_dev [n][3] doubles on the device, group g = rows [group_off_dev[g], group_off_dev[g + 1]);
+ * ref_centroid_host [3] on the host; out_dev [n_groups][3] = {count, centroid distance, max pair distance}.
+ * Needs no handle; `stream` is a cudaStream_t. */
+int dp_pointcloud_stats(const double* xyz_dev, const int32_t* group_off_dev, int32_t n_groups,
+                        const double* ref_centroid_host, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
