@@ -367,7 +367,8 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     DP_CHECK(ecap < (int64_t)2147483000, DP_ERR_INVALID, "edge capacity %lld exceeds int32 indexing", (long long)ecap);
     // segmented-sum scheme of the tcgen05 edge kernel (common.cuh): contiguous lanes for full-atom pockets (the same
     // size criterion as the cell-list graph builder), round-robin tiles with per-unit partial rows for Calpha pockets
-    p.seg_lanes = h->seg_mode == 2 || (h->seg_mode == 0 && p.max_nodes >= 512);
+    // (and for Calpha batches too large for the per-unit bookkeeping: agg_src encodes at most 2^20 units)
+    p.seg_lanes = h->seg_mode == 2 || (h->seg_mode == 0 && (p.max_nodes >= 512 || ecap / UNIT_TC + 2 >= (int64_t)(1 << 20)));
     p.n_lanes = p.seg_lanes ? 4 * h->sm_count : 0;
     DP_CHECK(p.n_lanes <= MAX_LANES, DP_ERR_INVALID, "%d SMs: more segmented-sum lanes than agg_src can encode", h->sm_count);
     DP_CHECK((ecap / UNIT_TC + 2) * (int64_t)(p.seg_lanes ? p.n_lanes : 1) < (int64_t)2147483000, DP_ERR_INVALID,
