@@ -1,4 +1,5 @@
-// K2 / K3 — the fused edge kernel on the 5th-generation tensor cores (DP_BF16 / DP_F16).
+// K2 / K3 — the fused edge kernel on the 5th-generation tensor cores (DP_BF16 / DP_F16 / DP_F16_FAST; arithmetic
+// modes: tc_common.cuh MODE_*; work split over CTAs and the atomic-free segmented sum: common.cuh "segmented sum").
 //
 //   message mode : GCL.edge_model + attention gate + CSR segmented sum   (egnn_new.py:31-52, 276-285)
 //   coord mode   : EquivariantUpdate.coord_mlp up to its per-edge scalar  (egnn_new.py:87-91)

@@ -7,7 +7,7 @@
 //                                                     this block's coordinate MLP — W1 [h_i; h_j; e] = W1a h_i +
 //                                                     W1b h_j + W1c e, so the H x H products are per node
 //
-// One CTA per 96-node tile runs the three GEMMs back to back without leaving the SM: the activations
+// One CTA per node tile (capacity 96, sized to fill whole waves of SMs) runs the three GEMMs back to back without leaving the SM: the activations
 // of each stage are written by the epilogue straight into the next stage's swizzled K-major B tile in
 // shared memory (never to HBM), accumulators live in TMEM (2 x 192 columns), and the weight panels
 // (32 KB each: 256 out channels x 64 K, pre-swizzled bf16/f16) stream through a 4-slot ring filled by
@@ -17,7 +17,8 @@
 //
 //   warps 0-15  compute : stage [h | agg] -> bf16 tiles; the three epilogues
 //   warp  16    TMA     : one thread streams the weight panels through the ring
-//   warp  17    MMA     : one thread issues tcgen05.mma (M=128, N=96, K=16), commits to mbarriers
+//   warp  17    MMA     : one thread issues tcgen05.mma (M=128, N=tile nodes rounded up to 16, K=16), commits to mbarriers
+// node_pair_kernel (below) is the CTA-pair variant: cluster of two, tcgen05 cta_group::2, half of every weight panel per CTA.
 #include "tc_common.cuh"
 
 namespace {
