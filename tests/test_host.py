@@ -109,3 +109,32 @@ def test_conditional_ddpm_error_conventions():
     with pytest.raises(ValueError):          # en_diffusion.py:64-77 norm-value sanity check
         ConditionalDDPM(dyn, 8, 20, 3, [[1.0]], timesteps=50, noise_schedule="cosine",
                         noise_precision=1e-4, loss_type="l2", norm_values=(1.0, 4.0))
+
+
+def test_precision_modes_match_the_header_enum():
+    """config.PRECISION_MODES (the names the Python mirror and the CLI accept) against dp_precision in the header."""
+    from cmd_gen_b200.config import PRECISION_MODES
+    header = open(os.path.join(ROOT, "include", "diffphar_b200.h")).read()
+    enum = dict((n, int(v)) for n, v in re.findall(r"\b(DP_(?:FP32|TF32|BF16|F16|F16_FAST|F16_FAST32))\s*=\s*(\d+)", header))
+    want = {"fp32": "DP_FP32", "tf32": "DP_TF32", "bf16": "DP_BF16", "f16": "DP_F16", "f16fast": "DP_F16_FAST",
+            "f16fast32": "DP_F16_FAST32"}
+    assert set(PRECISION_MODES) == set(want)
+    for name, sym in want.items():
+        assert PRECISION_MODES[name] == enum[sym], name
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """The product path has no fallback: a missing build raises (also through the DIFFPHAR_LIB A/B override)."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("DIFFPHAR_LIB", str(tmp_path / "no_such_build.so"))
+    with pytest.raises(_lib.DiffPharError):
+        _lib.load_library()
+    monkeypatch.delenv("DIFFPHAR_LIB")
+    monkeypatch.setattr(_lib, "_lib", None)
+    assert _lib.load_library() is not None
+
+
+def test_analysis_has_no_cpu_fallback(lib):
+    from cmd_gen_b200.analysis import phar_statistics
+    with pytest.raises(_lib.DiffPharError):
+        phar_statistics({"Molecule_0": {"Donor": [[0.0, 0.0, 0.0]]}}, [0.0, 0.0, 0.0], device="cpu")
