@@ -254,7 +254,7 @@ struct dp_handle {
     int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
     int seg_mode = 0;                  // DIFFPHAR_SEG: 0 automatic, 1 units, 2 lanes (Plan::seg_lanes)
     int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
-    int early_fill = 0;                // DIFFPHAR_EARLY_FILL: see EdgeArgs::early_fill
+    int tma_fill = 1;                  // DIFFPHAR_TMA_FILL=0: resident weights through LDG + tcgen05.st (A/B; EdgeArgs::tma_fill)
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
     int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells
@@ -314,7 +314,7 @@ struct EdgeArgs {
     int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
     int contig;                                      // tcgen05 path: 1 = contiguous lane ranges, 0 = round-robin 64-edge tiles (Plan::seg_lanes)
-    int early_fill;                                  // tcgen05 path: weights -> tensor memory ahead of the grid dependency / edge count
+    int tma_fill;                                    // tcgen05 path: resident weights through TMA + tcgen05.cp instead of LDG + tcgen05.st
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)

@@ -143,6 +143,13 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// shared memory -> tensor memory, asynchronous (tensor-core proxy, ordered with the same thread's later tcgen05.mma):
+// 128 rows x 256 bits of the K-major operand tile the descriptor names land on lanes 0..127, 8 consecutive columns —
+// the layout a .ts MMA reads its A operand in (K = 16 16-bit elements per row)
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc)
+{
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // registers -> 32 lanes x 32 consecutive columns (thread = TMEM lane)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
 {

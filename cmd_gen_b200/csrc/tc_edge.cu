@@ -77,6 +77,7 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     float gate[EPI_WARPS][GROUP_EDGES];
     float touch[PRO_WARPS][32];                   // cp.async landing pad of the L1 row prefetch (never read)
     unsigned long long bar_w;
+    unsigned long long bar_wload, bar_wdone;          // a.tma_fill: weight panels landed in shared memory / copied to tensor memory
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
     unsigned long long bar_tfull[N_TS], bar_tempty[N_TS];
     uint32_t tmem_holder;
@@ -128,9 +129,23 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == MMA_WARP * 32) trace_mark(a.trace, 1, 62, 0);                              // kernel entry
 
-    // ---- launch-invariant prologue (overlaps the previous kernel's tail under programmatic dependent launch)
+    // The edge count (and, for the round-robin split, the producers' first-tile metadata: loaded speculatively — the
+    // arrays hold ecap entries — and masked once E has arrived) is requested before anything else, so that its L2
+    // round trip overlaps the prologue (barrier init, tensor-memory allocation): 1 k cycles of every launch.  The
+    // grid dependency therefore sits at the very top (a no-op without programmatic dependent launch).
+    pdl_launch_dependents();
+    pdl_wait();                                       // from here on: data written by earlier kernels of the step
+    int s_row = 0, s_col = 0; float s_d0 = 0.f;
+    if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+        const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
+        if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
+    }
+    const int E = *a.n_edges;
+
+    // ---- prologue
     if (tid == 0) {
         mbar_init(smem_u32(&s.bar_w), EPI_WARPS);              // every epilogue warp fills its share of tensor memory
+        mbar_init(smem_u32(&s.bar_wload), 1); mbar_init(smem_u32(&s.bar_wdone), 1);
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
         for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
         fence_barrier_init();
@@ -142,13 +157,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     const uint32_t tmem_w = s.tmem_holder;                   // resident weights
     const uint32_t tmem_base = tmem_w + W_COLS;              // accumulator stages
     static_assert(W_COLS + N_TS * TS_COLS <= TMEM_COLS, "tensor memory budget");
-    pdl_launch_dependents();
-    // Resident weights: thread (q, lane) of epilogue group gi owns row c = 128 (gi & 1) + 32 q + lane of the [out][in]
-    // matrix = TMEM lane 32 q + lane of M-half gi & 1, K panels 2 (gi >> 1) and 2 (gi >> 1) + 1.  The 128 K elements are
-    // read from the swizzled panel image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 64 packed
-    // 32-bit columns.  Launch-invariant data: with a.early_fill the fill runs ahead of the grid dependency and of
-    // the edge count (all 148 CTAs pull the same 128 KB at once: ~19 MB through L2, the largest part of the
-    // pipeline fill), otherwise after them and only in CTAs that have tiles.
+    // Resident weights, load / store path (a.tma_fill = 0; the default goes through TMA + tcgen05.cp in the MMA warp):
+    // thread (q, lane) of epilogue group gi owns row c = 128 (gi & 1) + 32 q + lane of the [out][in] matrix = TMEM
+    // lane 32 q + lane of M-half gi & 1, K panels 2 (gi >> 1) and 2 (gi >> 1) + 1.  The 128 K elements are read from
+    // the swizzled panel image (chunk c of a row sits at chunk c ^ (row % 8)) and stored as 64 packed 32-bit columns.
+    // All 148 CTAs pull the same 128 KB at once (~19 MB through L2) and 16 warps of weight loads sit in the SM's
+    // load queues ahead of the producers' first gathers: 9 k cycles of pipeline fill.
     auto fill_weights = [&]() {
         const int q = wid & 3, gi = wid >> 2;
         const int mh = gi & 1, r = 128 * mh + 32 * q + lane;
@@ -168,20 +182,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.bar_w));
     };
-    if (a.early_fill && wid < EPI_WARPS) fill_weights();
-    pdl_wait();                                       // from here on: data written by earlier kernels of the step
     // Work split (common.cuh, "segmented sum of the tcgen05 edge kernel"):
-    //   a.contig = 0 (Calpha pockets): tile t = 64 consecutive edges, CTA t mod gridDim; the first tile's metadata does
-    //     not wait for the edge count (loaded speculatively: the arrays hold ecap entries; masked once E has arrived);
+    //   a.contig = 0 (Calpha pockets): tile t = 64 consecutive edges, CTA t mod gridDim (its first tile's metadata was
+    //     requested speculatively at the top of the kernel);
     //   a.contig = 1 (full-atom pockets): the U 16-edge units are cut into 4 x gridDim contiguous balanced lanes;
     //     epilogue group g (and the two producer warps that feed it) walks lane 4 blockIdx + g in order, one unit per
     //     tile, and the running sum of a CSR row stays in the group's registers from tile to tile.
-    int s_row = 0, s_col = 0; float s_d0 = 0.f;
-    if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
-        const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
-        if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
-    }
-    const int E = *a.n_edges;
     const unsigned U = (unsigned)((E + UNIT_TC - 1) / UNIT_TC), L = 4u * gridDim.x;
     // tiles of this CTA.  Lanes: its longest lane; lane lengths are floor(U / L) or ceil(U / L), so ceil(U / L) is exact
     // for every CTA that has a long lane and one (empty, skipped by has_unit) tile too many for the others — which
@@ -204,7 +210,36 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const uint32_t tw = warp_uniform(tmem_w), td = warp_uniform(tmem_base);
             const uint32_t x0 = warp_uniform(smem_u32(s.x[0]));
             if (lane == 0) trace_mark(a.trace, 1, 63, 0);
-            if (my_tiles > 0) mbar_wait(bar_w, 0);                     // weights are in tensor memory
+            if (a.tma_fill && my_tiles > 0) {
+                // Resident weights without the load / store units: four bulk copies bring the 128 KB image into the
+                // activation stages 1-3 and the gate-reduce buffer (all idle until the first tile is through), 32
+                // tcgen05.cp move it on to tensor memory (128 rows x 16 K per copy: the A-operand layout of the .ts
+                // MMAs), and the commit frees the buffers.  The producers' first loads no longer queue behind 16 warps
+                // of weight loads.
+                const uint32_t wl = smem_u32(&s.bar_wload);
+                const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
+                if (elect_one()) {
+                    mbar_expect_tx(wl, 4 * W_PANEL_BYTES);
+#pragma unroll
+                    for (int kp = 0; kp < 4; ++kp) bulk_g2s(dst[kp], w_img + (size_t)kp * W_PANEL_BYTES, W_PANEL_BYTES, wl);
+                }
+                __syncwarp();
+                mbar_wait(wl, 0);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kp = 0; kp < 4; ++kp)
+#pragma unroll
+                        for (int ks = 0; ks < PANEL_K / 16; ++ks)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh)
+                                tmem_cp_128x256b(tw + hh * 128 + kp * 32 + ks * 8, make_desc(dst[kp] + hh * (128 * 128) + ks * 32));
+                    umma_commit(smem_u32(&s.bar_wdone));
+                }
+                __syncwarp();
+            } else if (my_tiles > 0) {
+                mbar_wait(bar_w, 0);                                   // weights are in tensor memory
+            }
             if (lane == 0) trace_mark(a.trace, 1, 63, 1);
             for (int it = 0; it < my_tiles; ++it) {
                 const int xs = it % N_XS, ts = it % N_TS;
@@ -315,6 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
             touch_rows(n_row);
             mbar_wait_relaxed<EDGE_PRODUCER_SLEEP_NS>(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);   // up to 3 tiles ahead: a late wake-up costs nothing
+            if (a.tma_fill && it == 1) mbar_wait_relaxed(smem_u32(&s.bar_wdone), 0);    // stages 1-3 carried the weight panels
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
             unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
             uint32_t m_rd = 0u;
@@ -389,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* redw = s.red[ew];
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
-        if (!a.early_fill && my_tiles > 0) fill_weights();
+        if (!a.tma_fill && my_tiles > 0) fill_weights();
         const int unit0 = unit_base(gi), n_units = unit_count(gi);                      // this group's units
         float s0 = 0.f, s1 = 0.f;                                                        // running sum of the current CSR row: carried across tiles
         for (int it = 0; it < my_tiles; ++it) {
