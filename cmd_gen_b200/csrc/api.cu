@@ -554,7 +554,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
         e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
-        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.tma_fill = h->tma_fill; e.contig = p.seg_lanes;
+        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.tma_fill = h->tma_fill; e.dbg = h->dbg; e.contig = p.seg_lanes;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
         e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
@@ -580,7 +580,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
             q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
-            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.contig = p.seg_lanes;
+            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;

@@ -314,6 +314,7 @@ struct EdgeArgs {
     int n_moving;                                    // rows [0, n_moving) changed coordinates since the graph build
     const int* n_edges;                              // device scalar: edges to process
     int contig;                                      // tcgen05 path: 1 = contiguous lane ranges, 0 = round-robin 64-edge tiles (Plan::seg_lanes)
+    int dbg;                                         // timing experiments (DIFFPHAR_DBG bits; results are wrong), 0 in production
     int tma_fill;                                    // tcgen05 path: resident weights through TMA + tcgen05.cp instead of LDG + tcgen05.st
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)

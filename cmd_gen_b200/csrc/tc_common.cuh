@@ -222,6 +222,12 @@ __device__ __forceinline__ void ldg4_if(uint4& v, const void* p, bool take)
         "@q ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
         "}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((int)take));
 }
+__device__ __forceinline__ uint4 ldg_u4(const void* p)
+{
+    uint4 v;
+    asm("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint4 ldg_na_u4(const void* p)
 {
     uint4 v;

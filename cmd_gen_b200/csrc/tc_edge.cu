@@ -75,7 +75,6 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     float red[EPI_WARPS][32 * RED_STRIDE];        // 40 KB: per-warp [channel pair][16 edges (+4 pad)]
     float part[2][EPI_WARPS][GROUP_EDGES];        // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][GROUP_EDGES];
-    float touch[PRO_WARPS][32];                   // cp.async landing pad of the L1 row prefetch (never read)
     unsigned long long bar_w;
     unsigned long long bar_wload, bar_wdone;          // a.tma_fill: weight panels landed in shared memory / copied to tensor memory
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
@@ -266,8 +265,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         //   * Pb rows (512 B of f16) stream through an 8-slot register pipeline (no L1 allocation): the slot of
         //     edge i is refilled with edge i of the NEXT tile right after edge i is computed, so a gather has a
         //     whole tile to land.  Pa + Pb is added in f16x2, widened once, the rest of the layer runs in fp32.
-        //   * Pa changes once per CSR row run: a warp-uniform branch reloads it; the rows a tile will need are
-        //     pulled into L1 one tile ahead (one 32-sector touch per row), so the reload is an L1 hit.
+        //   * Pa changes once per CSR row run: a predicated 128-bit reload (an L1 hit when a neighbouring warp's chunk
+        //     of the same row came first, else L2).  An explicit L1 prefetch of the next tile's rows (cp.async touch, one
+        //     loop iteration per distinct row) cost more serial issue time than the misses it removed: -2.4 % step time
+        //     without it (profiles/r04d_producer_dbg.txt).
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_producer(MODE)));
         const int pw = wid - EPI_WARPS;
@@ -289,28 +290,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         const __half* pq = reinterpret_cast<const __half*>(a.p);                         // f16 rows, pre-scaled by 1/2 (tc_node.cu)
         const __half* pa_base = pq + a.off_a + 8 * lane;
         const __half* pb_base = pq + a.off_b + 8 * lane;
-        const __half* pa_touch = pq + a.off_a + 16 * (lane & 15);                        // lanes 0-15 touch the 16 sectors of a 512 B row
         // Slots without an edge (past E, or past the end of a shorter lane) are processed as edge (0, 0): finite garbage in columns nobody reads.
         int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
         auto load_rc = [&](int it, int& r, int& c, float& d0) {
             const int e = (unit0 + it * unit_step) * UNIT_TC + e_off;
             r = 0; c = 0; d0 = 0.f;
             if (it < n_units && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
-        };
-        // L1 prefetch of the distinct rows of a group: one cp.async.ca per row, lane l < 16 pulling sector l of the
-        // 512 B row through L1 into a scratch word — no destination register, so nothing ever waits on it
-        const uint32_t scratch = smem_u32(&s.touch[pw][lane]);
-        auto touch_rows = [&](int rows_on_lanes) {
-            const int prev = __shfl_up_sync(0xffffffffu, rows_on_lanes, 1);
-            const unsigned fm0 = __ballot_sync(0xffffffffu, lane < 8 && (lane == 0 || rows_on_lanes != prev));
-            unsigned fm = fm0;
-            while (fm) {
-                const int i = __ffs(fm) - 1;
-                fm &= fm - 1;
-                const int r = __shfl_sync(0xffffffffu, rows_on_lanes, i);
-                if (lane < 16)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(scratch), "l"(row_ptr(pa_touch, (uint32_t)r, ldp_b)) : "memory");
-            }
         };
         // metadata runs two tiles ahead: m_ = this tile (complete), n_ = next tile (r2 pending), f_ = loading
         auto dist2 = [&](float xr0, float xr1, float xr2, float xc0, float xc1, float xc2) {
@@ -328,13 +313,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 #pragma unroll
         for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile's gathers go out first
             pb[u] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, m_col, u), ldp_b));
-        touch_rows(m_row);
         load_rc(1, n_row, n_col, n_d0);
         m_r2 = m_d0;
         if (m_row < a.n_moving || m_col < a.n_moving)                                    // an endpoint moved since the graph build
             m_r2 = dist2(a.x[3 * m_row], a.x[3 * m_row + 1], a.x[3 * m_row + 2], a.x[3 * m_col], a.x[3 * m_col + 1], a.x[3 * m_col + 2]);
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);                                          // Pa of the current CSR row run (8 halves)
-        int cur_row = -1;
+        // Pa of the current CSR row run (8 halves).  It changes once per run; the reload for the NEXT edge's row is issued
+        // before this edge's arithmetic (its row is known from the metadata lanes), so an L2 round trip hides behind one
+        // edge of work instead of sitting in the chain
+        int cur_row = __shfl_sync(0xffffffffu, m_row, 0);
+        uint4 cur = ldg_u4(row_ptr(pa_base, (uint32_t)cur_row, ldp_b));
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
         const int l74 = (lane & 7) << 4;
 
@@ -348,7 +335,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const int xr_i = n_moving ? 3 * n_row : 0, xc_i = n_moving ? 3 * n_col : 0;
             const float xr0 = a.x[xr_i], xr1 = a.x[xr_i + 1], xr2 = a.x[xr_i + 2];
             const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
-            touch_rows(n_row);
             mbar_wait_relaxed<EDGE_PRODUCER_SLEEP_NS>(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);   // up to 3 tiles ahead: a late wake-up costs nothing
             if (a.tma_fill && it == 1) mbar_wait_relaxed(smem_u32(&s.bar_wdone), 0);    // stages 1-3 carried the weight panels
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
@@ -361,9 +347,17 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int row = __shfl_sync(0xffffffffu, m_row, i);
-                ldg4_if(cur, row_ptr(pa_base, (uint32_t)row, ldp_b), row != cur_row);             // new CSR row run: Pa (L1 hit, touched a tile ago)
-                cur_row = row;
+                const int next_row = i < 7 ? __shfl_sync(0xffffffffu, m_row, i + 1) : __shfl_sync(0xffffffffu, n_row, 0);
+                if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
+                uint4 nxt = cur;
+                ldg4_if(nxt, row_ptr(pa_base, (uint32_t)next_row, ldp_b), next_row != cur_row && !(a.dbg & 2));   // next edge starts a new row run
+                if (TRACE && i < 2) {                                                    // timeline only: when Pa / Pb of this edge have landed
+                    uint32_t t0, t1;
+                    asm volatile("mov.b32 %0, %1;" : "=r"(t0) : "r"(cur.x));
+                    if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 8 + 4 * i);
+                    asm volatile("mov.b32 %0, %1;" : "=r"(t1) : "r"(pb[i].x));
+                    if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 9 + 4 * i);
+                }
                 const uint32_t ca[4] = {cur.x, cur.y, cur.z, cur.w}, cb[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
                 uint32_t o[4];
                 if (PACKED) {
@@ -399,6 +393,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) = make_uint4(o[0], o[1], o[2], o[3]);   // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
                 // refill the slot with the same edge of the next tile
                 pb[i] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, n_col, i), ldp_b));
+                if (TRACE && i < 2) { asm volatile("" ::: "memory"); if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 10 + 4 * i); }
+                cur = nxt; cur_row = next_row;
             }
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
             fence_proxy_async();                                                        // generic-proxy writes -> async proxy
@@ -409,7 +405,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             m_r2 = n_moving ? dist2(xr0, xr1, xr2, xc0, xc1, xc2) : n_d0;
             n_row = f_row; n_col = f_col; n_d0 = f_d0;
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ================================ epilogue ================================
         if (regs_epilogue(MODE) > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));

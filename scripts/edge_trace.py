@@ -34,7 +34,7 @@ rc = h.lib.dp_debug_trace(h.h, buf, n)
 assert rc == 0, h.lib.dp_last_error()
 tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(6)]
 t0 = min(v for r in tr for it in r for v in it if v > 0)
-names = {0: ["start", "xempty", "half", "-", "-", "-", "arrive", "e0 meta", "e0 pa", "e0 math", "e0 refill", "e1 meta", "e1 pa", "e1 math", "e1 refill"],
+names = {0: ["start", "xempty", "half", "-", "-", "-", "arrive", "e0 row", "e0 Pa", "e0 Pb", "e0 done", "e1 row", "e1 Pa", "e1 Pb", "e1 done"],
          1: ["start", "full", "tempty", "issued"],
          2: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"],
          3: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"]}
