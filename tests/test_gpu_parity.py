@@ -27,11 +27,12 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None):
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None):
     """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH);
-    seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG)."""
+    seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
+    node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel."""
     import os
-    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg}
+    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill}
     old = {k: os.environ.pop(k, None) for k in forced}
     for k, v in forced.items():
         if v:
@@ -282,6 +283,36 @@ def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg)
         # same inputs twice: the segmented sum has a fixed order (no atomics) -> bit-identical
         a2, r2 = h.dynamics_forward(z, xr, t)
         assert torch.equal(a2.cpu(), a) and torch.equal(r2.cpu(), r)
+
+
+@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}])
+def test_alternative_kernel_paths_match_the_default(switch):
+    """The switchable kernel variants kept for A/B runs (CTA-pair node kernel with tcgen05 cta_group::2 and DSMEM bulk
+    exchange; LDG + tcgen05.st weight fill of the edge kernel) against the default path on a ragged batch: same
+    arithmetic per element, so the results agree to the f16 operand rounding of the differing summation orders."""
+    cfg = DynamicsConfig(n_layers=3)
+    sizes, counts = [150, 97, 211, 1, 180, 64, 33], [8, 4, 12, 1, 6, 9, 2]
+    pocket = make_pocket_batch(sizes, 20, seed=41)
+    gen = torch.Generator().manual_seed(42)
+    mask_p = torch.repeat_interleave(torch.arange(len(counts)), torch.tensor(counts))
+    com = torch.stack([pocket["x"][pocket["mask"] == b].mean(0) for b in range(len(sizes))])
+    z = torch.cat([com[mask_p] + 4.0 * torch.randn(sum(counts), 3, generator=gen), torch.randn(sum(counts), 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    t = torch.full((len(sizes),), 0.6)
+    ref = make_handle(cfg, 0, "f16fast")
+    ref.plan(counts, sizes)
+    rp, rr = ref.dynamics_forward(z, xr, t)
+    alt = make_handle(cfg, 0, "f16fast", **switch)
+    alt.plan(counts, sizes)
+    ap, ar = alt.dynamics_forward(z, xr, t)
+    assert alt.flags().nan_resets == 0 and alt.flags().last_n_edges == ref.flags().last_n_edges
+    rp, rr, ap, ar = rp.cpu(), rr.cpu(), ap.cpu(), ar.cpu()
+    tol_h, tol_v = TC_TOL["f16fast"]
+    assert (ap[:, 3:] - rp[:, 3:]).abs().max() <= tol_h * max(1.0, float(rp[:, 3:].abs().max()))
+    assert (ar[:, 3:] - rr[:, 3:]).abs().max() <= tol_h * max(1.0, float(rr[:, 3:].abs().max()))
+    assert (ap[:, :3] - rp[:, :3]).abs().max() <= 1e-5 * 80 + tol_v * float(rp[:, :3].abs().max())
+    if "node_pair" not in switch:                   # the weight fill changes no arithmetic at all: bit-identical
+        assert torch.equal(ap, rp) and torch.equal(ar, rr)
 
 
 def test_dynamics_module_api_and_kwargs():
