@@ -349,8 +349,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             for (int i = 0; i < 8; ++i) {
                 const int next_row = i < 7 ? __shfl_sync(0xffffffffu, m_row, i + 1) : __shfl_sync(0xffffffffu, n_row, 0);
                 if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
-                uint4 nxt = cur;
-                ldg4_if(nxt, row_ptr(pa_base, (uint32_t)next_row, ldp_b), next_row != cur_row && !(a.dbg & 2));   // next edge starts a new row run
+                // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
+                // (a predicated load straight into a copy of `cur` chains every reload behind the previous one's arrival)
+                const bool new_run = next_row != cur_row && !(a.dbg & 2);                 // next edge starts a new row run
+                uint4 fresh = make_uint4(0u, 0u, 0u, 0u);
+                ldg4_if(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
+                const uint4 nxt = make_uint4(new_run ? fresh.x : cur.x, new_run ? fresh.y : cur.y, new_run ? fresh.z : cur.z, new_run ? fresh.w : cur.w);
                 if (TRACE && i < 2) {                                                    // timeline only: when Pa / Pb of this edge have landed
                     uint32_t t0, t1;
                     asm volatile("mov.b32 %0, %1;" : "=r"(t0) : "r"(cur.x));
