@@ -391,6 +391,12 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     prof_begin(h, PROF_GRAPH, st);
+    // Lane-range segmented sum with fewer units than lanes (E < 16 x lanes: small graphs): some lanes own no unit and
+    // never store their partial rows, but a row that crosses such a lane still adds them (agg_src names a lane RANGE).
+    // The lane boundaries move with E from one denoiser call to the next, so those rows must not keep an older call's
+    // sums: cleared here, once per graph build (1.2 MB; the lanes that do own units rewrite theirs in every launch).
+    if (p.seg_lanes && p.n_lanes > 0)
+        DP_CUDA(cudaMemsetAsync(p.partials, 0, (size_t)2 * p.n_lanes * H * sizeof(float), st));
     if (p.use_cells) {
         DP_CUDA(launch_kernel(h->pdl, cell_build_kernel, dim3(p.B), dim3(256), 0, st, a));
         DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<false>, dim3(grid), dim3(256), 0, st, a));
