@@ -21,6 +21,7 @@ EXPORTS = [
     "dp_set_weights", "dp_set_precision", "dp_plan", "dp_build_edges", "dp_get_graph", "dp_dynamics_forward",
     "dp_ddpm_update", "dp_set_step_table", "dp_sample", "dp_sample_host", "dp_get_flags", "dp_reset_flags",
     "dp_launch_count", "dp_profile_enable", "dp_profile_read", "dp_pointcloud_stats",
+    "dp_sample_ex", "dp_fill_noise", "dp_sample_host_seeded", "dp_graph_captures",
 ]
 
 
@@ -35,6 +36,12 @@ class DpConfig(C.Structure):
 class DpFlags(C.Structure):
     _fields_ = [("nan_resets", C.c_int32), ("edge_overflow", C.c_int32), ("max_mean_rel_err", C.c_float),
                 ("last_max_cog", C.c_float), ("last_n_edges", C.c_int64), ("last_n_edges_phar", C.c_int64)]
+
+
+class DpSampleOpts(C.Structure):
+    _fields_ = [("noise_dev", C.c_void_p), ("seed", C.c_uint64), ("sample_ids_host", C.c_void_p),
+                ("return_frames", C.c_int32), ("norm_x", C.c_float), ("norm_h", C.c_float), ("bias_h", C.c_float),
+                ("frames_phar_dev", C.c_void_p), ("frames_pocket_dev", C.c_void_p)]
 
 
 class DiffPharError(RuntimeError):
@@ -79,6 +86,11 @@ def load_library():
     lib.dp_profile_enable.argtypes = [vp, i32]
     lib.dp_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.dp_pointcloud_stats.argtypes = [vp, vp, i32, C.POINTER(C.c_double), vp, vp]
+    lib.dp_sample_ex.argtypes = [vp, vp, C.POINTER(DpSampleOpts), vp, vp]
+    lib.dp_fill_noise.argtypes = [vp, C.c_uint64, vp, i32, vp, vp]
+    lib.dp_sample_host_seeded.argtypes = [vp, vp, C.c_uint64, vp, vp, vp]
+    lib.dp_graph_captures.argtypes = [vp]
+    lib.dp_graph_captures.restype = i64
     _lib = lib
     return lib
 
@@ -123,6 +135,7 @@ class Handle:
         _check(self.lib.dp_create(C.byref(c), idx, C.byref(h)))
         self.h = h
         self.layout = None
+        self._grown = False
         self._keep = []
 
     def __del__(self):
@@ -151,9 +164,18 @@ class Handle:
         key = (tuple(pc.tolist()), tuple(rc.tolist()), int(edge_capacity))
         if key == self.layout:
             return
+        if self.layout is not None and key[:2] == self.layout[:2] and edge_capacity == 0 and self._grown:
+            return          # the automatic capacity overflowed on this layout before: keep the grown plan
         _check(self.lib.dp_plan(self.h, pc.numel(), _ptr(pc), _ptr(rc), int(edge_capacity)))
         self.layout = key
+        self._grown = False
         self.n_phar, self.n_res = int(pc.sum()), int(rc.sum())
+
+    def grow_edge_capacity(self, edge_capacity: int):
+        """Re-plan the current layout with a larger edge buffer (after dp_flags.edge_overflow reported the need)."""
+        pc, rc, _ = self.layout
+        self.plan(pc, rc, edge_capacity=int(edge_capacity))
+        self._grown = True
 
     def set_step_table(self, rows: torch.Tensor, final: torch.Tensor):
         rows = rows.detach().to("cpu", torch.float32).contiguous()
@@ -192,14 +214,56 @@ class Handle:
         _check(self.lib.dp_ddpm_update(self.h, int(kind), float(a), float(c), float(sigma), _ptr(z), _ptr(pocket),
                                        _ptr(eps_hat), _ptr(noise), _stream(self.device)))
 
-    def sample(self, xh_pocket: torch.Tensor, noise: torch.Tensor):
-        """xh_pocket (normalised, device, modified in place), noise [n_steps+2, N_p, 3+P] -> out_phar."""
+    def sample(self, xh_pocket: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 0, sample_ids=None,
+               return_frames: int = 1, norm=(1.0, 1.0, 0.0)):
+        """xh_pocket (normalised, device, modified in place) -> out_phar [N_p, 3+P] = (x_final | z0 features).
+
+        noise [n_steps+2, N_p, 3+P] injects the gaussian draws; noise=None draws them on the device from the
+        counter-based generator keyed by (seed, global sample id) — sample_ids [n_samples] int64, default 0..n-1.
+        return_frames > 1 also returns (frames_phar [F, N_p, 3+P], frames_pocket [F, N_r, 3+R]), un-normalised with
+        norm = (norm_values[0], norm_values[1], norm_biases[1]); frame 0 is for the caller to fill."""
         assert xh_pocket.is_cuda and xh_pocket.dtype == torch.float32 and xh_pocket.is_contiguous()
-        noise = _dev_f32(noise, self.device)
         out = torch.empty((self.n_phar, 3 + self.cfg.phar_nf), device=self.device, dtype=torch.float32)
-        self._keep = [noise]
-        _check(self.lib.dp_sample(self.h, _ptr(xh_pocket), _ptr(noise), _ptr(out), _stream(self.device)))
+        o = DpSampleOpts()
+        keep = []
+        if noise is not None:
+            noise = _dev_f32(noise, self.device)
+            keep.append(noise)
+            o.noise_dev = noise.data_ptr()
+        else:
+            o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+            if sample_ids is not None:
+                ids = torch.as_tensor(sample_ids, dtype=torch.int64, device="cpu").contiguous()
+                keep.append(ids)
+                o.sample_ids_host = ids.data_ptr()
+        o.return_frames = int(return_frames)
+        frames = None
+        if return_frames > 1:
+            o.norm_x, o.norm_h, o.bias_h = (float(v) for v in norm)
+            frames = (torch.zeros((return_frames, self.n_phar, 3 + self.cfg.phar_nf), device=self.device),
+                      torch.zeros((return_frames, self.n_res, 3 + self.cfg.residue_nf), device=self.device))
+            o.frames_phar_dev, o.frames_pocket_dev = frames[0].data_ptr(), frames[1].data_ptr()
+        self._keep = keep
+        _check(self.lib.dp_sample_ex(self.h, _ptr(xh_pocket), C.byref(o), _ptr(out), _stream(self.device)))
+        return out if frames is None else (out, frames[0], frames[1])
+
+    def fill_noise(self, n_draws: int, seed: int, sample_ids=None) -> torch.Tensor:
+        """[n_draws, N_p, 3+P] draws of the device generator (what sample(noise=None, seed=...) consumes)."""
+        out = torch.empty((n_draws, self.n_phar, 3 + self.cfg.phar_nf), device=self.device, dtype=torch.float32)
+        ids = None if sample_ids is None else torch.as_tensor(sample_ids, dtype=torch.int64, device="cpu").contiguous()
+        _check(self.lib.dp_fill_noise(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ids), int(n_draws), _ptr(out),
+                                      _stream(self.device)))
         return out
+
+    def sample_host_seeded(self, xh_pocket_host, seed, out_phar_host, pocket_out_host=None, sample_ids=None):
+        for t in (xh_pocket_host, out_phar_host):
+            assert (not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous()
+        ids = None if sample_ids is None else torch.as_tensor(sample_ids, dtype=torch.int64, device="cpu").contiguous()
+        _check(self.lib.dp_sample_host_seeded(self.h, _ptr(xh_pocket_host), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ids),
+                                              _ptr(out_phar_host), _ptr(pocket_out_host)))
+
+    def graph_captures(self) -> int:
+        return int(self.lib.dp_graph_captures(self.h))
 
     def sample_host(self, xh_pocket_host: torch.Tensor, noise_host: torch.Tensor, out_phar_host: torch.Tensor,
                     pocket_out_host: Optional[torch.Tensor] = None):

@@ -2,6 +2,7 @@
 // and the orchestration of one denoiser evaluation / one reverse-diffusion run.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -81,6 +82,35 @@ static void free_bag(std::vector<void*>& bag)
     bag.clear();
 }
 
+int GrowBuf::reserve(size_t bytes, bool* moved)
+{
+    if (moved) *moved = false;
+    if (bytes <= cap && p) return DP_OK;
+    DP_CUDA(cudaDeviceSynchronize());                      // earlier work may still read the old allocation
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 4 + 256;
+    DP_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    if (moved) *moved = true;
+    return DP_OK;
+}
+
+// Carves the per-plan buffers out of the handle's arena: first pass sizes, second pass assigns.
+namespace {
+struct Carver {
+    struct Slot { void** out; size_t off; };
+    std::vector<Slot> slots;
+    size_t total = 0;
+    template <typename T> void take(T** out, size_t count)
+    {
+        total = (total + 255) & ~(size_t)255;
+        slots.push_back({reinterpret_cast<void**>(out), total});
+        total += (count ? count : 1) * sizeof(T);
+    }
+    void assign(void* base) { for (auto& sl : slots) *sl.out = static_cast<unsigned char*>(base) + sl.off; }
+};
+}  // namespace
+
 // --------------------------------------------------------------------------------------
 // create / destroy
 // --------------------------------------------------------------------------------------
@@ -135,10 +165,14 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     return DP_OK;
 }
 
+static void drop_graph(dp_handle* h)
+{
+    if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+}
+
 static void free_plan(dp_handle* h)
 {
-    if (h->plan.step_graph) { cudaGraphExecDestroy(h->plan.step_graph); }
-    free_bag(h->plan.allocations);
+    drop_graph(h);
     h->plan = Plan();
     h->has_plan = false;
 }
@@ -148,6 +182,7 @@ extern "C" int dp_destroy(dp_handle* h)
     if (!h) return DP_OK;
     cudaSetDevice(h->device);
     free_plan(h);
+    h->arena.release(); h->steps.release(); h->noise.release(); h->frames.release();
     free_bag(h->w.allocations);
     tc_free_weights(h);
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -322,7 +357,7 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
     h->tc_host.clear();
     h->tc_host.shrink_to_fit();
     h->has_weights = true;
-    if (h->plan.step_graph) { cudaGraphExecDestroy(h->plan.step_graph); h->plan.step_graph = nullptr; }
+    drop_graph(h);
     return DP_OK;
 }
 
@@ -337,12 +372,20 @@ extern "C" int dp_set_precision(dp_handle* h, int precision)
 // --------------------------------------------------------------------------------------
 // plan
 // --------------------------------------------------------------------------------------
+static int bind_step_table(dp_handle* h);
+
 extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, const int32_t* res_counts, int64_t edge_capacity)
 {
     DP_CHECK(h && phar_counts && res_counts, DP_ERR_INVALID, "dp_plan: null argument");
     DP_CHECK(B > 0, DP_ERR_INVALID, "dp_plan: n_samples must be positive");
     DP_CUDA(cudaSetDevice(h->device));
-    DP_CUDA(cudaDeviceSynchronize());
+    // the same layout again (a pocket list with repeated shapes, the mirror's per-call plan): nothing to do, the
+    // captured step graph stays valid
+    if (h->has_plan && h->plan.B == B && h->plan.ecap_request == edge_capacity &&
+        std::equal(phar_counts, phar_counts + B, h->plan.phar_counts_host.begin()) &&
+        std::equal(res_counts, res_counts + B, h->plan.res_counts_host.begin()))
+        return DP_OK;
+    DP_CUDA(cudaDeviceSynchronize());                          // the previous layout's work is done before its buffers are re-carved
     free_plan(h);
     Plan& p = h->plan;
     const dp_config& c = h->cfg;
@@ -359,6 +402,9 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     }
     p.B = B; p.Np = poff[B]; p.Nr = roff[B]; p.N = p.Np + p.Nr;
     DP_CHECK(p.N > 0, DP_ERR_INVALID, "dp_plan: empty batch");
+    p.phar_counts_host.assign(phar_counts, phar_counts + B);
+    p.res_counts_host.assign(res_counts, res_counts + B);
+    p.ecap_request = edge_capacity;
     int64_t ecap = edge_capacity;
     if (ecap <= 0) {
         const double guess = (double)p.N * 128.0 > 65536.0 ? (double)p.N * 128.0 : 65536.0;
@@ -378,72 +424,87 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     DP_CHECK((int64_t)p.N + 2 * (ecap / UNIT_TC + 2 + MAX_LANES) < (int64_t)2147483000, DP_ERR_INVALID, "batch too large for int32 row indexing");
     p.Ecap = ecap;
     std::vector<int> sample_of(p.N);
+    std::vector<int64_t> ids(B);
     for (int b = 0; b < B; ++b) {
+        ids[b] = b;
         for (int i = poff[b]; i < poff[b + 1]; ++i) sample_of[i] = b;
         for (int i = roff[b]; i < roff[b + 1]; ++i) sample_of[p.Np + i] = b;
     }
-    auto& bag = p.allocations;
-    int rc = 0;
     const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
     // partial rows: per 64-edge tile on the FFMA path, per lane on the tcgen05 path (a handful of KB instead of E / 8 KB)
     size_t units = (size_t)(ecap / UNIT_F32 + 2);
     if (p.seg_lanes && (size_t)p.n_lanes > units) units = (size_t)p.n_lanes;
     if (!p.seg_lanes) units = (size_t)(ecap / UNIT_TC + 2);
-#define ALLOC(ptr, count) if ((rc = dev_alloc(bag, &(ptr), (size_t)(count)))) return rc
-    ALLOC(p.phar_off, B + 1); ALLOC(p.res_off, B + 1); ALLOC(p.sample_of, p.N);
-    ALLOC(p.deg, p.N); ALLOC(p.rowptr, p.N + 1); ALLOC(p.agg_src, p.N);
-    ALLOC(p.col, ecap); ALLOC(p.erow, ecap); ALLOC(p.edst, ecap); ALLOC(p.d0, ecap); ALLOC(p.escal, ecap);
-    ALLOC(p.counts, 4);
     // bucketed cell list: pays off once a sample has more nodes than a handful of warp sweeps (full-atom pockets)
     p.use_cells = c.edge_cutoff > 0.f && p.max_nodes <= CELL_SAMPLE_MAX_NODES &&
                   (h->graph_mode == 2 || (h->graph_mode == 0 && p.max_nodes >= 512));
+    // One arena for every per-plan buffer: a layout that fits the arena re-carves it (no cudaMalloc / cudaFree, each of
+    // which synchronises the device), so walking a pocket list re-plans in microseconds.
+    Carver cv;
+    cv.take(&p.phar_off, B + 1); cv.take(&p.res_off, B + 1); cv.take(&p.sample_of, p.N); cv.take(&p.sample_ids, B);
+    cv.take(&p.deg, p.N); cv.take(&p.rowptr, p.N + 1); cv.take(&p.agg_src, p.N);
+    cv.take(&p.col, ecap); cv.take(&p.erow, ecap); cv.take(&p.edst, ecap); cv.take(&p.d0, ecap); cv.take(&p.escal, ecap);
+    cv.take(&p.counts, 4);
     if (p.use_cells) {
-        ALLOC(p.cell_start, (size_t)B * (CELLS_MAX + 1)); ALLOC(p.cell_nodes, p.N); ALLOC(p.cell_grid, (size_t)B * 8);
+        cv.take(&p.cell_start, (size_t)B * (CELLS_MAX + 1)); cv.take(&p.cell_nodes, p.N); cv.take(&p.cell_grid, (size_t)B * 8);
         p.bitmap_words = (p.max_nodes + 31) / 32;
-        ALLOC(p.row_bitmap, (size_t)p.N * p.bitmap_words);     // 8 MB at config 3: the fill pass skips the bucket search
+        cv.take(&p.row_bitmap, (size_t)p.N * p.bitmap_words);  // 8 MB at config 3: the fill pass skips the bucket search
     }
-    ALLOC(p.h, (size_t)p.N * H); ALLOC(p.tbuf, (size_t)p.N * H); ALLOC(p.h_base, (size_t)p.Nr * H);
-    ALLOC(p.agg, ((size_t)p.N + units * 2) * H);          // [agg rows | partial rows] contiguous (graph.cu edge_dst)
+    cv.take(&p.h, (size_t)p.N * H); cv.take(&p.tbuf, (size_t)p.N * H); cv.take(&p.h_base, (size_t)p.Nr * H);
+    cv.take(&p.agg, ((size_t)p.N + units * 2) * H);        // [agg rows | partial rows] contiguous (graph.cu edge_dst)
+    cv.take(&p.pq, (size_t)p.N * 4 * H);
+    cv.take(&p.x_in, (size_t)p.N * 3); cv.take(&p.x_a, (size_t)p.N * 3); cv.take(&p.x_b, (size_t)p.N * 3);
+    cv.take(&p.z, (size_t)p.Np * PW); cv.take(&p.eps_hat, (size_t)p.Np * PW); cv.take(&p.pocket, (size_t)p.Nr * RW);
+    cv.take(&p.out_buf, (size_t)p.Np * PW);
+    cv.take(&p.t_const, 4); cv.take(&p.step_idx, 1); cv.take(&p.nan_flag, 2);
+    int rc = h->arena.reserve(cv.total);
+    if (rc) return rc;
+    cv.assign(h->arena.p);
     p.partials = p.agg + (size_t)p.N * H;
-    ALLOC(p.pq, (size_t)p.N * 4 * H);
-    ALLOC(p.x_in, (size_t)p.N * 3); ALLOC(p.x_a, (size_t)p.N * 3); ALLOC(p.x_b, (size_t)p.N * 3);
-    ALLOC(p.z, (size_t)p.Np * PW); ALLOC(p.eps_hat, (size_t)p.Np * PW); ALLOC(p.pocket, (size_t)p.Nr * RW);
-    ALLOC(p.t_const, 4); ALLOC(p.step_idx, 1); ALLOC(p.nan_flag, 2);
-#undef ALLOC
     DP_CUDA(cudaMemcpy(p.phar_off, poff.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(p.res_off, roff.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(p.sample_of, sample_of.data(), (size_t)p.N * sizeof(int), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemcpy(p.sample_ids, ids.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemset(p.counts, 0, 4 * sizeof(int)));
     DP_CUDA(cudaMemset(p.nan_flag, 0, 2 * sizeof(int)));
     DP_CUDA(cudaMemset(p.step_idx, 0, sizeof(int)));
     DP_CUDA(cudaMemset(p.t_const, 0, 4 * sizeof(float)));
     h->has_plan = true;
-    if (h->n_steps > 0) {   // re-upload the step table into the new plan
-        std::vector<float> rows = h->step_rows_host;
-        float fin[4]; memcpy(fin, h->final_host, sizeof(fin));
-        return dp_set_step_table(h, rows.data(), h->n_steps, fin);
-    }
+    return bind_step_table(h);
+}
+
+// The step table lives in a handle-owned buffer (it does not depend on the batch layout): a new plan only re-binds it.
+static int bind_step_table(dp_handle* h)
+{
+    Plan& p = h->plan;
+    if (h->n_steps <= 0 || !h->steps.p) { p.step_rows = nullptr; p.stats = nullptr; p.stats_cap = 0; return DP_OK; }
+    p.step_rows = reinterpret_cast<float*>(h->steps.p);
+    p.stats = p.step_rows + (((size_t)h->n_steps * 4 + 63) & ~(size_t)63);
+    p.stats_cap = h->n_steps + 2;
     return DP_OK;
 }
 
 extern "C" int dp_set_step_table(dp_handle* h, const float* rows, int32_t n_steps, const float* fin)
 {
     DP_CHECK(h && rows && fin && n_steps > 0, DP_ERR_INVALID, "dp_set_step_table: bad argument");
+    DP_CUDA(cudaSetDevice(h->device));
+    // unchanged table (the mirror sets it on every sample_given_pocket call): keep buffers and the captured graph
+    if (h->n_steps == n_steps && h->steps.p && h->step_rows_host.size() == (size_t)n_steps * 4 &&
+        !memcmp(h->step_rows_host.data(), rows, (size_t)n_steps * 4 * sizeof(float)) && !memcmp(h->final_host, fin, 4 * sizeof(float)))
+        return bind_step_table(h);
     if (rows != h->step_rows_host.data()) h->step_rows_host.assign(rows, rows + (size_t)n_steps * 4);
     memcpy(h->final_host, fin, 4 * sizeof(float));
+    const bool new_count = n_steps != h->n_steps;
     h->n_steps = n_steps;
-    if (!h->has_plan) return DP_OK;
-    Plan& p = h->plan;
-    DP_CUDA(cudaSetDevice(h->device));
+    const size_t rows_f = ((size_t)n_steps * 4 + 63) & ~(size_t)63, stats_f = (size_t)(n_steps + 2) * 2;
+    bool moved = false;
     DP_CUDA(cudaDeviceSynchronize());
-    int rc = 0;
-    if ((rc = dev_alloc(p.allocations, &p.step_rows, (size_t)n_steps * 4))) return rc;
-    if ((rc = dev_alloc(p.allocations, &p.stats, (size_t)(n_steps + 2) * 2))) return rc;
-    p.stats_cap = n_steps + 2;
-    DP_CUDA(cudaMemcpy(p.step_rows, h->step_rows_host.data(), (size_t)n_steps * 4 * sizeof(float), cudaMemcpyHostToDevice));
-    DP_CUDA(cudaMemset(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float)));
-    if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
-    return DP_OK;
+    int rc = h->steps.reserve((rows_f + stats_f) * sizeof(float), &moved);
+    if (rc) return rc;
+    DP_CUDA(cudaMemcpy(h->steps.p, h->step_rows_host.data(), (size_t)n_steps * 4 * sizeof(float), cudaMemcpyHostToDevice));
+    DP_CUDA(cudaMemset(reinterpret_cast<float*>(h->steps.p) + rows_f, 0, stats_f * sizeof(float)));
+    if (moved || new_count) drop_graph(h);                    // the graph bakes the table pointer and the step count
+    return bind_step_table(h);
 }
 
 // --------------------------------------------------------------------------------------
@@ -473,7 +534,7 @@ extern "C" int dp_get_graph(dp_handle* h, const int32_t** rowptr, const int32_t*
     int counts[4];
     DP_CUDA(cudaMemcpyAsync(counts, h->plan.counts, sizeof(counts), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     DP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    DP_CHECK(counts[2] == 0, DP_ERR_CAPACITY, "graph has %d edges but edge_capacity is %lld", counts[0], (long long)h->plan.Ecap);
+    DP_CHECK(counts[2] == 0, DP_ERR_CAPACITY, "graph has %d edges but edge_capacity is %lld", counts[2], (long long)h->plan.Ecap);
     if (rowptr) *rowptr = h->plan.rowptr;
     if (col) *col = h->plan.col;
     if (n_edges) *n_edges = counts[0];
@@ -627,7 +688,13 @@ extern "C" int dp_ddpm_update(dp_handle* h, int32_t kind, float a, float c, floa
     return launch_ddpm(h, d, (cudaStream_t)stream);
 }
 
-static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise, cudaStream_t st)
+struct FrameSpec {                      // return_frames > 1 (conditional_model.py:439-442): where the DDPM update drops its frames
+    int return_frames = 0;              // 0: none
+    float* phar = nullptr; float* pocket = nullptr;
+    float norm_x = 1.f, norm_h = 1.f, bias_h = 0.f;
+};
+
+static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise, const FrameSpec& fs, cudaStream_t st)
 {
     Plan& p = h->plan; const dp_config& c = h->cfg;
     const int PW = 3 + c.phar_nf;
@@ -638,19 +705,22 @@ static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise
     d.z = p.z; d.pocket = pocket; d.eps_hat = p.eps_hat; d.noise = noise;
     d.noise_step_stride = (int64_t)p.Np * PW; d.noise_step_base = 1;
     d.stat_base = 0; d.stat_index = -1; d.advance = 1;
+    if (fs.return_frames > 1) {
+        d.frames_phar = fs.phar; d.frames_pocket = fs.pocket; d.return_frames = fs.return_frames; d.n_steps = h->n_steps;
+        d.norm_x = fs.norm_x; d.norm_h = fs.norm_h; d.bias_h = fs.bias_h;
+    }
     return launch_ddpm(h, d, st);
 }
 
-extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float* out_phar, void* stream)
+// The loop of sample_given_pocket on handle-owned buffers only (plan.pocket, handle noise / frame buffers): the
+// captured step graph therefore never bakes a caller pointer and survives any number of calls with fresh tensors.
+static int sample_core(dp_handle* h, const FrameSpec& fs, cudaStream_t st)
 {
-    int rc = require(h, true, true);
-    if (rc) return rc;
-    DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
-    DP_CHECK(pocket && noise && out_phar, DP_ERR_INVALID, "dp_sample: null tensor");
     Plan& p = h->plan; const dp_config& c = h->cfg;
-    cudaStream_t st = (cudaStream_t)stream;
     const int PW = 3 + c.phar_nf;
-    const size_t zbytes = (size_t)p.Np * PW * sizeof(float);
+    float* pocket = p.pocket;
+    const float* noise = reinterpret_cast<const float*>(h->noise.p);
+    int rc = 0;
     DP_CUDA(cudaMemsetAsync(p.step_idx, 0, sizeof(int), st));
     DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
     DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, sizeof(int), st));
@@ -665,68 +735,168 @@ extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float*
 
     if (h->profile) {
         for (int k = 0; k < h->n_steps; ++k)
-            if ((rc = sampler_step_launches(h, pocket, noise, st))) return rc;
+            if ((rc = sampler_step_launches(h, pocket, noise, fs, st))) return rc;
     } else {
-        if (!p.step_graph || p.graph_noise != (void*)noise || p.graph_precision != h->precision ||
-            p.graph_pocket != (void*)pocket) {
-            if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
+        const int want_frames = fs.return_frames > 1 ? fs.return_frames : 0;
+        if (!h->step_graph || h->graph_precision != h->precision || h->graph_frames != want_frames) {
+            drop_graph(h);
             const int64_t before = h->launches;
             cudaGraph_t g = nullptr;
             // the legacy default stream cannot be captured: record on a handle-owned stream and
             // replay the instantiated graph on the caller's stream
             if (!h->capture_stream) DP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
             DP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
-            rc = sampler_step_launches(h, pocket, noise, h->capture_stream);
+            rc = sampler_step_launches(h, pocket, noise, fs, h->capture_stream);
             cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             DP_CUDA(ce);
-            p.graph_launches = h->launches - before;
+            h->graph_launches = h->launches - before;
             h->launches = before;
-            DP_CUDA(cudaGraphInstantiate(&p.step_graph, g, 0));
+            DP_CUDA(cudaGraphInstantiate(&h->step_graph, g, 0));
             cudaGraphDestroy(g);
-            p.graph_noise = (void*)noise; p.graph_precision = h->precision; p.graph_pocket = (void*)pocket;
+            h->graph_precision = h->precision; h->graph_frames = want_frames;
+            h->graph_captures += 1;
         }
-        for (int k = 0; k < h->n_steps; ++k) DP_CUDA(cudaGraphLaunch(p.step_graph, st));
-        h->launches += p.graph_launches * h->n_steps;
+        for (int k = 0; k < h->n_steps; ++k) DP_CUDA(cudaGraphLaunch(h->step_graph, st));
+        h->launches += h->graph_launches * h->n_steps;
     }
     // p(x | z0): conditional_model.py:108-131
     DP_CUDA(cudaMemcpyAsync(p.t_const, &h->final_host[0], sizeof(float), cudaMemcpyHostToDevice, st));
     if ((rc = run_denoiser(h, p.z, pocket, p.t_const, nullptr, 0, 0, p.eps_hat, nullptr, st, true))) return rc;
-    DP_CUDA(cudaMemcpyAsync(out_phar, p.z, zbytes, cudaMemcpyDeviceToDevice, st));          // keeps z0's feature columns
+    DP_CUDA(cudaMemcpyAsync(p.out_buf, p.z, (size_t)p.Np * PW * sizeof(float), cudaMemcpyDeviceToDevice, st));   // keeps z0's feature columns
     DdpmArgs df{};
     df.kind = 1; df.a = h->final_host[1]; df.c = h->final_host[2]; df.sigma = h->final_host[3];
     df.z = p.z; df.pocket = pocket; df.eps_hat = p.eps_hat;
     df.noise = noise + (size_t)(h->n_steps + 1) * p.Np * PW; df.stat_index = h->n_steps; df.advance = 0;
     if ((rc = launch_ddpm(h, df, st))) return rc;
-    DP_CUDA(cudaMemcpy2DAsync(out_phar, PW * sizeof(float), p.z, PW * sizeof(float), 3 * sizeof(float), p.Np,
+    DP_CUDA(cudaMemcpy2DAsync(p.out_buf, PW * sizeof(float), p.z, PW * sizeof(float), 3 * sizeof(float), p.Np,
                               cudaMemcpyDeviceToDevice, st));
     return DP_OK;
 }
 
-extern "C" int dp_sample_host(dp_handle* h, const float* pocket_host, const float* noise_host, float* out_phar_host,
-                              float* pocket_out_host)
+// noise / frame buffers of the current (plan, step table); a moved buffer invalidates the captured graph
+static int reserve_run_buffers(dp_handle* h, int return_frames)
+{
+    Plan& p = h->plan; const dp_config& c = h->cfg;
+    const size_t PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
+    bool moved = false;
+    int rc = h->noise.reserve((size_t)(h->n_steps + 2) * p.Np * PW * sizeof(float), &moved);
+    if (rc) return rc;
+    if (moved) drop_graph(h);
+    if (return_frames > 1) {
+        rc = h->frames.reserve((size_t)return_frames * ((size_t)p.Np * PW + (size_t)p.Nr * RW) * sizeof(float), &moved);
+        if (rc) return rc;
+        if (moved) drop_graph(h);
+    }
+    return DP_OK;
+}
+
+extern "C" int dp_fill_noise(dp_handle* h, uint64_t seed, const int64_t* sample_ids_host, int32_t n_draws, float* noise_dev, void* stream)
+{
+    int rc = require(h, false, true);
+    if (rc) return rc;
+    DP_CHECK(n_draws > 0 && noise_dev, DP_ERR_INVALID, "dp_fill_noise: bad argument");
+    Plan& p = h->plan;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sample_ids_host) {
+        DP_CUDA(cudaMemcpyAsync(p.sample_ids, sample_ids_host, (size_t)p.B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        DP_CUDA(cudaStreamSynchronize(st));                // the host array may be a temporary of the caller
+    }
+    return launch_fill_noise(h, seed, n_draws, noise_dev, st);
+}
+
+extern "C" int dp_sample_ex(dp_handle* h, float* pocket, const dp_sample_opts* o, float* out_phar, void* stream)
 {
     int rc = require(h, true, true);
     if (rc) return rc;
-    DP_CHECK(pocket_host && noise_host && out_phar_host, DP_ERR_INVALID, "dp_sample_host: null buffer");
+    DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
+    DP_CHECK(pocket && o && out_phar, DP_ERR_INVALID, "dp_sample_ex: null argument");
+    const int F = o->return_frames > 1 ? o->return_frames : 1;
+    DP_CHECK(F <= h->n_steps && h->n_steps % F == 0, DP_ERR_INVALID,
+             "return_frames %d must divide the %d sampling steps", F, h->n_steps);   // conditional_model.py:395-396
+    DP_CHECK(F == 1 || (o->frames_phar_dev && o->frames_pocket_dev), DP_ERR_INVALID, "dp_sample_ex: frame buffers missing");
+    Plan& p = h->plan; const dp_config& c = h->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
+    if ((rc = reserve_run_buffers(h, F))) return rc;
+    const size_t noise_count = (size_t)(h->n_steps + 2) * p.Np * PW;
+    if (o->noise_dev) {
+        if (o->noise_dev != h->noise.p)
+            DP_CUDA(cudaMemcpyAsync(h->noise.p, o->noise_dev, noise_count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if ((rc = dp_fill_noise(h, o->seed, o->sample_ids_host, h->n_steps + 2, reinterpret_cast<float*>(h->noise.p), stream))) {
+        return rc;
+    }
+    if (pocket != p.pocket)
+        DP_CUDA(cudaMemcpyAsync(p.pocket, pocket, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    FrameSpec fs;
+    if (F > 1) {
+        fs.return_frames = F; fs.norm_x = o->norm_x; fs.norm_h = o->norm_h; fs.bias_h = o->bias_h;
+        fs.phar = reinterpret_cast<float*>(h->frames.p);
+        fs.pocket = fs.phar + (size_t)F * p.Np * PW;
+    }
+    if ((rc = sample_core(h, fs, st))) return rc;
+    if (pocket != p.pocket)
+        DP_CUDA(cudaMemcpyAsync(pocket, p.pocket, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out_phar != p.out_buf)
+        DP_CUDA(cudaMemcpyAsync(out_phar, p.out_buf, (size_t)p.Np * PW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (F > 1) {
+        DP_CUDA(cudaMemcpyAsync(o->frames_phar_dev, fs.phar, (size_t)F * p.Np * PW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        DP_CUDA(cudaMemcpyAsync(o->frames_pocket_dev, fs.pocket, (size_t)F * p.Nr * RW * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return DP_OK;
+}
+
+extern "C" int dp_sample(dp_handle* h, float* pocket, const float* noise, float* out_phar, void* stream)
+{
+    DP_CHECK(noise, DP_ERR_INVALID, "dp_sample: null noise (dp_sample_ex draws counter-based noise on the device)");
+    dp_sample_opts o{};
+    o.noise_dev = noise; o.return_frames = 1;
+    return dp_sample_ex(h, pocket, &o, out_phar, stream);
+}
+
+static int sample_host_common(dp_handle* h, const float* pocket_host, const float* noise_host, uint64_t seed,
+                              const int64_t* sample_ids_host, float* out_phar_host, float* pocket_out_host)
+{
+    int rc = require(h, true, true);
+    if (rc) return rc;
+    DP_CHECK(pocket_host && out_phar_host, DP_ERR_INVALID, "dp_sample_host: null buffer");
+    DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
     Plan& p = h->plan; const dp_config& c = h->cfg;
     const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;
+    if ((rc = reserve_run_buffers(h, 1))) return rc;
     const size_t noise_count = (size_t)(h->n_steps + 2) * p.Np * PW;
-    if (!p.noise_buf || p.noise_buf_count < noise_count) {
-        if ((rc = dev_alloc(p.allocations, &p.noise_buf, noise_count))) return rc;
-        if (!p.out_buf && (rc = dev_alloc(p.allocations, &p.out_buf, (size_t)p.Np * PW))) return rc;
-        p.noise_buf_count = noise_count;
-    }
     cudaStream_t st = 0;
     DP_CUDA(cudaMemcpyAsync(p.pocket, pocket_host, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyHostToDevice, st));
-    DP_CUDA(cudaMemcpyAsync(p.noise_buf, noise_host, noise_count * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = dp_sample(h, p.pocket, p.noise_buf, p.out_buf, st))) return rc;
+    dp_sample_opts o{};
+    o.return_frames = 1;
+    if (noise_host) {
+        DP_CUDA(cudaMemcpyAsync(h->noise.p, noise_host, noise_count * sizeof(float), cudaMemcpyHostToDevice, st));
+        o.noise_dev = reinterpret_cast<const float*>(h->noise.p);
+    } else {
+        o.seed = seed; o.sample_ids_host = sample_ids_host;
+    }
+    if ((rc = dp_sample_ex(h, p.pocket, &o, p.out_buf, st))) return rc;
     DP_CUDA(cudaMemcpyAsync(out_phar_host, p.out_buf, (size_t)p.Np * PW * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (pocket_out_host)
         DP_CUDA(cudaMemcpyAsync(pocket_out_host, p.pocket, (size_t)p.Nr * RW * sizeof(float), cudaMemcpyDeviceToHost, st));
     DP_CUDA(cudaStreamSynchronize(st));
     return DP_OK;
 }
+
+extern "C" int dp_sample_host(dp_handle* h, const float* pocket_host, const float* noise_host, float* out_phar_host,
+                              float* pocket_out_host)
+{
+    DP_CHECK(noise_host, DP_ERR_INVALID, "dp_sample_host: null noise (dp_sample_host_seeded draws it on the device)");
+    return sample_host_common(h, pocket_host, noise_host, 0, nullptr, out_phar_host, pocket_out_host);
+}
+
+extern "C" int dp_sample_host_seeded(dp_handle* h, const float* pocket_host, uint64_t seed, const int64_t* sample_ids_host,
+                                     float* out_phar_host, float* pocket_out_host)
+{
+    return sample_host_common(h, pocket_host, nullptr, seed, sample_ids_host, out_phar_host, pocket_out_host);
+}
+
+extern "C" int64_t dp_graph_captures(const dp_handle* h) { return h ? h->graph_captures : 0; }
 
 // --------------------------------------------------------------------------------------
 // flags / counters / profiling

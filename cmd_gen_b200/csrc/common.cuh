@@ -231,19 +231,23 @@ struct Plan {
     float* pocket = nullptr;     // [Nr][3+R]
     float* t_const = nullptr;    // [1]
     int* step_idx = nullptr;     // [1]
-    float* step_rows = nullptr;  // [n_steps][4]
-    float* stats = nullptr;      // [n_steps+2][2] (max |sum x|, max |x|) as float bits
+    float* step_rows = nullptr;  // [n_steps][4]   (handle-owned: dp_handle::steps)
+    float* stats = nullptr;      // [n_steps+2][2] (max |sum x|, max |x|) as float bits (handle-owned)
     int stats_cap = 0;
     int* nan_flag = nullptr;     // [2]: current-call flag, sticky count
-    std::vector<void*> allocations;
-    cudaGraphExec_t step_graph = nullptr;
-    void* graph_noise = nullptr; // pointers baked into the captured graph
-    void* graph_pocket = nullptr;
-    int graph_precision = -1;
-    int64_t graph_launches = 0;  // kernels per replay of step_graph
-    // dp_sample_host staging
-    float* noise_buf = nullptr; size_t noise_buf_count = 0;
-    float* out_buf = nullptr;
+    int64_t* sample_ids = nullptr;   // [B] global id of each sample: selects its counter-based noise stream (small.cu)
+    float* out_buf = nullptr;    // [Np][3+P] dp_sample_host staging
+    // layout as planned (host copies: an identical dp_plan call keeps the captured graph)
+    std::vector<int> phar_counts_host, res_counts_host;
+    int64_t ecap_request = 0;
+};
+
+// A device buffer that only ever grows: re-planning a smaller or equal batch costs no cudaMalloc / cudaFree
+// (each is a device-wide synchronisation) — what a pocket-list workload (BASELINE config 4) does per pocket.
+struct GrowBuf {
+    void* p = nullptr; size_t cap = 0;
+    int reserve(size_t bytes, bool* moved = nullptr);    // api.cu; 25 % headroom when it has to grow
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
 struct dp_handle {
@@ -265,6 +269,18 @@ struct dp_handle {
     std::vector<HostLinear> tc_host;   // indexed by lin_id (see run_denoiser)
     Plan plan;
     bool has_plan = false;
+    GrowBuf arena;                     // every per-plan buffer is carved out of this one allocation (dp_plan)
+    GrowBuf steps;                     // step table rows + guard statistics (dp_set_step_table)
+    GrowBuf noise;                     // [n_steps+2][Np][3+P]: the noise the captured step graph reads (injected noise is copied
+                                       // in, seeded noise is generated in place), so the graph never bakes a caller pointer
+    GrowBuf frames;                    // return_frames > 1: [frames][Np][3+P] then [frames][Nr][3+R], un-normalised
+    // the captured denoising step (one per handle; re-captured when something baked into it changes)
+    cudaGraphExec_t step_graph = nullptr;
+    int graph_precision = -1;
+    int graph_frames = 0;              // return_frames the graph was captured for (0: no frame output)
+    int64_t graph_launches = 0;        // kernels per replay of step_graph
+    int64_t graph_captures = 0;        // how many times the step graph was (re)captured (tests: re-planning the same
+                                       // layout or sampling with fresh caller tensors must not re-capture)
     std::vector<float> step_rows_host;
     float final_host[4] = {0, 0, 0, 0};
     int n_steps = 0;
@@ -342,8 +358,13 @@ struct DdpmArgs {
     int stat_index;                           // stats row (table == null), else *step_idx + stat_base
     int stat_base;
     int advance;                              // 1: increment *step_idx afterwards (separate tiny kernel)
+    // return_frames > 1 (conditional_model.py:439-442): the step with s = n_steps - 1 - *step_idx writes the
+    // un-normalised state (en_diffusion.py:891-906) to frame s * return_frames / n_steps when that division is exact
+    float* frames_phar; float* frames_pocket; int return_frames; int n_steps;
+    float norm_x, norm_h, bias_h;
 };
 int launch_ddpm(dp_handle* h, const DdpmArgs& a, cudaStream_t st);
+int launch_fill_noise(dp_handle* h, uint64_t seed, int n_draws, float* noise_dev, cudaStream_t st);
 int launch_pocket_com_init(dp_handle* h, float* z, const float* pocket, cudaStream_t st);
 
 // tc_weights.cu (tcgen05)

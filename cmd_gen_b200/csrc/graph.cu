@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
     pdl_launch_dependents();
     pdl_wait();
     if (tid == 0) carry_s = 0;
+    const int cap = ecap < 2147483647LL ? (int)ecap : 2147483647;
     __syncthreads();
     for (int base = 0; base < N; base += 1024 * PER) {
         const int i0 = base + tid * PER;
@@ -355,21 +356,24 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
         int run = carry + (wid ? warp_sums[wid - 1] : 0) + incl - sum;
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
-            if (i0 + q < N) rowptr[i0 + q] = run;
+            if (i0 + q < N) rowptr[i0 + q] = run < cap ? run : cap;      // clamped: see the overflow note below
             run += v[q];
         }
         __syncthreads();
         if (tid == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
+    // Overflow (more edges than the plan's capacity): every consumer indexes the per-edge arrays by rowptr / counts,
+    // so both are published CLAMPED to the capacity — the truncated graph is wrong but memory-safe — and counts[2]
+    // carries the true edge count (non-zero = overflow; the caller re-plans with at least that capacity).
     if (tid == 0) {
         const int E = carry_s;
-        rowptr[N] = E;
-        counts[0] = E;
-        if ((long long)E > ecap) counts[2] = 1;
+        rowptr[N] = E < cap ? E : cap;
+        counts[0] = E < cap ? E : cap;
+        if ((long long)E > ecap) counts[2] = E;
     }
     __syncthreads();
-    if (tid == 0) counts[1] = rowptr[Np];   // E_p: rows [0, Np) are the phar nodes
+    if (tid == 0) counts[1] = rowptr[Np];   // E_p: rows [0, Np) are the phar nodes (clamped like every rowptr entry)
 }
 
 }  // namespace

@@ -240,6 +240,7 @@ struct DdpmKArgs {
     const int* phar_off; const int* res_off;
     int P, R; int* nan_flag; float* stats;
     int* ticket;                                      // advance: the block that finishes last bumps *step_idx
+    int Np, Nr;                                       // totals: frame strides
 };
 
 __device__ __forceinline__ void atomic_max_pos(float* addr, float v)
@@ -260,14 +261,22 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
     int kind = d.kind; float A = d.a, C = d.c, S = d.sigma;
     const float* noise = d.noise;
     int stat_row = d.stat_index;
+    int frame = -1;                                   // frame index this step writes, -1: none
     if (d.table) {
         const int step = *d.step_idx;
+        if (d.frames_phar) {
+            const int s = d.n_steps - 1 - step;       // conditional_model.py:428, 440-441
+            if ((s * d.return_frames) % d.n_steps == 0) frame = (s * d.return_frames) / d.n_steps;
+        }
         const float* row = d.table + 4 * (size_t)step;
         kind = 0; A = row[1]; C = row[2]; S = row[3];
         noise = d.noise + (size_t)(step + d.noise_step_base) * d.noise_step_stride;
         stat_row = step + d.stat_base;
     }
     const bool nan = k.nan_flag[0] != 0;
+    // the sticky count behind the reference's 'Warning: detected nan, resetting EGNN output to zero.' (dynamics.py:129-131):
+    // the fused sampler never runs nan_fixup_kernel, so the update that consumes the flag counts it
+    if (nan && kind != 2 && b == 0 && tid == 0) k.nan_flag[1] += 1;
     float* mean = buf + (size_t)np * D;
     for (int idx = tid; idx < np * D; idx += blockDim.x) {
         const int c = idx % D;
@@ -304,11 +313,23 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
         float v = buf[idx];
         if (c < 3) v = __fsub_rn(v, mean[c]);
         d.z[(size_t)p0 * D + idx] = v;
+        if (frame >= 0)                               // unnormalize_z, en_diffusion.py:891-906
+            d.frames_phar[((size_t)frame * k.Np + p0) * D + idx] =
+                c < 3 ? __fmul_rn(v, d.norm_x) : __fadd_rn(__fmul_rn(v, d.norm_h), d.bias_h);
     }
     for (int idx = tid; idx < nr * 3; idx += blockDim.x) {
         const int i = idx / 3, c = idx - 3 * i;
         float* px = d.pocket + (size_t)(r0 + i) * RW + c;
         *px = __fsub_rn(*px, mean[c]);
+    }
+    if (frame >= 0) {
+        __syncthreads();                              // the translated coordinates of this sample's pocket rows
+        for (int idx = tid; idx < nr * RW; idx += blockDim.x) {
+            const int c = idx % RW;
+            const float v = d.pocket[(size_t)r0 * RW + idx];
+            d.frames_pocket[((size_t)frame * k.Nr + r0) * RW + idx] =
+                c < 3 ? __fmul_rn(v, d.norm_x) : __fadd_rn(__fmul_rn(v, d.norm_h), d.bias_h);
+        }
     }
     if (d.advance && tid == 0) {
         // every block read *step_idx before arriving here; the last one to arrive moves the sampler on
@@ -318,6 +339,49 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// Counter-based gaussian noise (replaces torch.randn in sample_gaussian, en_diffusion.py:946-949, when the caller
+// injects none): Philox4x32-10 keyed by the seed, counter = (quad of the sample's flat [n_p][3+P] block, draw index,
+// GLOBAL sample id), Box-Muller on the four words.  A sample's noise depends on its global id only — not on the batch
+// it is packed into or the GPU that runs it — so a sharded pocket list reproduces the single-GPU result bit for bit.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float2 box_muller(unsigned a, unsigned b)
+{
+    const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;      // (0, 1): 24 bits, never 0 or 1
+    const float u2 = ((float)(b >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    return make_float2(r * cs, r * sn);
+}
+
+__global__ void __launch_bounds__(128) fill_noise_kernel(float* noise, const int* phar_off, const long long* sample_ids,
+                                                         int Np, int D, unsigned seed_lo, unsigned seed_hi)
+{
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int p0 = phar_off[b], n = (phar_off[b + 1] - p0) * D;
+    const unsigned long long gid = (unsigned long long)sample_ids[b];
+    float* dst = noise + ((size_t)k * Np + p0) * D;
+    for (int q = threadIdx.x; 4 * q < n; q += blockDim.x) {
+        const uint4 w = philox4x32_10(make_uint4((unsigned)q, (unsigned)k, (unsigned)gid, (unsigned)(gid >> 32)), make_uint2(seed_lo, seed_hi));
+        const float2 g0 = box_muller(w.x, w.y), g1 = box_muller(w.z, w.w);
+        const float v[4] = {g0.x, g0.y, g1.x, g1.y};
+        for (int j = 0; j < 4; ++j)
+            if (4 * q + j < n) dst[4 * q + j] = v[j];
+    }
+}
 
 // mu of the initial draw: pocket COM per sample, zero features (conditional_model.py:412-414)
 __global__ void __launch_bounds__(128) pocket_com_init_kernel(float* z, const float* pocket, const int* phar_off,
@@ -417,13 +481,25 @@ int launch_ddpm(dp_handle* h, const DdpmArgs& d, cudaStream_t st)
     const Plan& p = h->plan; const dp_config& c = h->cfg;
     DdpmKArgs k;
     k.d = d; k.phar_off = p.phar_off; k.res_off = p.res_off; k.P = c.phar_nf; k.R = c.residue_nf;
-    k.nan_flag = p.nan_flag; k.stats = p.stats; k.ticket = p.counts + 3;
+    k.nan_flag = p.nan_flag; k.stats = p.stats; k.ticket = p.counts + 3; k.Np = p.Np; k.Nr = p.Nr;
     const size_t smem = ((size_t)p.max_phar * (3 + c.phar_nf) + 4) * sizeof(float);
     DP_CHECK(smem <= 48 * 1024, DP_ERR_INVALID, "ddpm: %d phar nodes in one sample exceed the shared-memory tile", p.max_phar);
     prof_begin(h, PROF_DDPM, st);
     DP_CUDA(launch_kernel(h->pdl, ddpm_kernel, dim3(p.B), dim3(128), smem, st, k));
     h->launches += 1;
     prof_end(h, st);
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+int launch_fill_noise(dp_handle* h, uint64_t seed, int n_draws, float* noise_dev, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    if (p.Np == 0) return DP_OK;
+    DP_CHECK(n_draws <= 65535, DP_ERR_INVALID, "dp_fill_noise: %d draws exceed the grid's y extent", n_draws);
+    fill_noise_kernel<<<dim3(p.B, n_draws), 128, 0, st>>>(noise_dev, p.phar_off, reinterpret_cast<const long long*>(p.sample_ids),
+                                                          p.Np, 3 + c.phar_nf, (unsigned)seed, (unsigned)(seed >> 32));
+    h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
 }

@@ -41,6 +41,9 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         self._check_norm_values()
         assert not self.dynamics.update_pocket_coords          # conditional_model.py:18
         self._tables = {}
+        self.stepwise = False           # True: drive the loop from the host through the per-step API (reference control flow)
+        self.noise_seed = None          # int: draw the sampler's noise with the library's counter-based device generator
+        self.sample_ids = None          # [n_samples] global sample ids selecting the noise streams (default 0..n-1)
 
     def _check_norm_values(self, num_stdevs=8):               # en_diffusion.py:64-77
         g0 = self.gamma(torch.zeros((1, 1)))
@@ -102,6 +105,24 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         return h
 
     @staticmethod
+    def _denoise(h, z, xh_pocket, t):
+        """One denoiser evaluation of the per-step API with the reference's guards (dynamics.py:129-131): the NaN
+        reset is reported, an edge-capacity overflow re-plans once and evaluates again."""
+        for attempt in range(2):
+            eps_hat, _ = h.dynamics_forward(z, xh_pocket, t, want_residues=False)
+            fl = h.flags()
+            if not fl.edge_overflow:
+                break
+            h.reset_flags()
+            if attempt == 1:
+                raise _lib.DiffPharError("edge buffer overflow persists after re-planning")
+            h.grow_edge_capacity(int(fl.edge_overflow * 1.25) + 1024)
+        if fl.nan_resets:
+            print('Warning: detected nan, resetting EGNN output to zero.')
+            h.reset_flags()
+        return eps_hat
+
+    @staticmethod
     def _scalar(v, what):
         v = v.reshape(-1)
         if v.numel() > 1 and not bool((v == v[0]).all()):
@@ -151,7 +172,7 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         sigma = sigma_ts * sigma_s / sigma_t
         n_samples = int(s.shape[0])
         h = self._planned_handle(zt_phar.device, phar_mask, pocket_mask, n_samples)
-        eps_hat, _ = h.dynamics_forward(zt_phar, xh0_pocket, t.to(torch.float32), want_residues=False)
+        eps_hat = self._denoise(h, zt_phar, xh0_pocket, t.to(torch.float32))
         eps = self.sample_gaussian(size=(len(phar_mask), self.n_dims + self.phar_nf), device=phar_mask.device)
         self.assert_mean_zero_with_mask(zt_phar[:, :self.n_dims], phar_mask)
         z = zt_phar.detach().to(torch.float32).contiguous().clone()
@@ -168,7 +189,7 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         gamma_0 = self.gamma(t_zeros)
         sigma_x = self.SNR(-0.5 * gamma_0)
         h = self._planned_handle(dev, phar_mask, pocket_mask, batch_size)
-        eps_hat, _ = h.dynamics_forward(z0_phar, xh0_pocket, t_zeros, want_residues=False)
+        eps_hat = self._denoise(h, z0_phar, xh0_pocket, t_zeros)
         net = eps_hat
         inv_alpha0 = 1. / self.alpha(gamma_0, target_tensor=net)
         sigma0 = self.sigma(gamma_0, target_tensor=net)
@@ -196,19 +217,33 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         _, pocket = self.normalize(pocket=pocket)
         xh0_pocket = torch.cat([pocket['x'], pocket['one_hot']], dim=1)
         phar_mask = num_nodes_to_batch_mask(n_samples, num_nodes_phar, device)
-        if return_frames != 1:
+        if self.stepwise:
             return self._sample_with_frames(pocket, xh0_pocket, phar_mask, n_samples, return_frames, timesteps)
 
         h = self._planned_handle(device, phar_mask, pocket['mask'], n_samples)
         tab = self._table(timesteps)
         h.set_step_table(tab.rows, tab.final)
-        noise = self._draw(timesteps + 2, (len(phar_mask), nd + self.phar_nf), device)
-        xh_pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
-        out = h.sample(xh_pocket, noise)                      # [N_p, 3+P] = (x_final | z0 features)
-
-        fl = h.flags()                                        # ONE host read for the whole run
-        if fl.edge_overflow:
-            raise _lib.DiffPharError("edge buffer overflow: re-plan with a larger edge_capacity")
+        # gaussian draws: torch's generator as in the reference (sample_gaussian, en_diffusion.py:946-949; also the hook
+        # the parity harness replaces), or — with `noise_seed` set — the library's counter-based device generator,
+        # whose draws depend on (seed, global sample id) only: the same sample comes out whatever the batching / sharding
+        noise = None if self.noise_seed is not None and 'sample_gaussian' not in self.__dict__ else \
+            self._draw(timesteps + 2, (len(phar_mask), nd + self.phar_nf), device)
+        norm = (float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]))
+        for attempt in range(2):
+            xh_pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
+            res = h.sample(xh_pocket, noise, seed=self.noise_seed or 0, sample_ids=self.sample_ids,
+                           return_frames=return_frames, norm=norm)
+            fl = h.flags()                                    # ONE host read for the whole run
+            if not fl.edge_overflow:
+                break
+            # the radius graph outgrew the planned edge capacity (the device truncated it, memory-safe): re-plan with
+            # the edge count it reported and run again on the same noise
+            h.reset_flags()
+            if attempt == 1:
+                raise _lib.DiffPharError(f"edge buffer overflow persists at capacity {cap}")
+            cap = int(fl.edge_overflow * 1.25) + 1024
+            h.grow_edge_capacity(cap)
+        out, frames_phar, frames_pocket = res if return_frames > 1 else (res, None, None)
         if fl.nan_resets:
             print('Warning: detected nan, resetting EGNN output to zero.')
         assert fl.max_mean_rel_err < 1e-2, f'Mean is not zero, relative_error {fl.max_mean_rel_err}'
@@ -218,16 +253,21 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         x_pocket, h_pocket = self.unnormalize(xh_pocket[:, :nd], xh_pocket[:, nd:])
         h_phar = F.one_hot(torch.argmax(h_phar, dim=1), self.phar_nf)
         self.assert_mean_zero_with_mask(x_phar, phar_mask)
-        max_cog = scatter_add(x_phar, phar_mask).abs().max().item()
-        if max_cog > 5e-2:
-            print(f'Warning CoG drift with error {max_cog:.3f}. Projecting the positions down.')
-            x_phar, x_pocket = self.remove_mean_batch(x_phar, x_pocket, phar_mask, pocket['mask'])
+        if return_frames == 1:                                # conditional_model.py:449-457
+            max_cog = scatter_add(x_phar, phar_mask).abs().max().item()
+            if max_cog > 5e-2:
+                print(f'Warning CoG drift with error {max_cog:.3f}. Projecting the positions down.')
+                x_phar, x_pocket = self.remove_mean_batch(x_phar, x_pocket, phar_mask, pocket['mask'])
         out_phar = torch.cat([x_phar, h_phar.to(x_phar.dtype)], dim=1)
         out_pocket = torch.cat([x_pocket, h_pocket], dim=1)
+        if return_frames > 1:                                 # frames were written inside the captured loop; frame 0 = the result
+            frames_phar[0], frames_pocket[0] = out_phar, out_pocket
+            return frames_phar, frames_pocket, phar_mask, pocket['mask']
         return out_phar, out_pocket, phar_mask, pocket['mask']
 
     def _sample_with_frames(self, pocket, xh0_pocket, phar_mask, n_samples, return_frames, timesteps):
-        """return_frames > 1: the loop is driven from the host, one fused step at a time."""
+        """The reference's loop driven from the host through the per-step API, one fused step at a time (kept for
+        callers that step the sampler themselves, and as the checker of the in-graph frame output)."""
         device = xh0_pocket.device
         nd = self.n_dims
         mu_x = scatter_mean(pocket['x'], pocket['mask'])

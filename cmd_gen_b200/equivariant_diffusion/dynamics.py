@@ -154,7 +154,14 @@ class EGNNDynamics(nn.Module):
         out_p, out_r = h.dynamics_forward(xh_phars, xh_residues, t.to(torch.float32), want_residues=True)
         fl = h.flags()
         if fl.edge_overflow:
-            raise _lib.DiffPharError("edge buffer overflow: re-plan with a larger edge_capacity")
+            # the device truncated the graph at the planned capacity (memory-safe, results invalid) and reported the
+            # edge count it needs: grow the plan once and evaluate again
+            h.reset_flags()
+            h.grow_edge_capacity(int(fl.edge_overflow * 1.25) + 1024)
+            out_p, out_r = h.dynamics_forward(xh_phars, xh_residues, t.to(torch.float32), want_residues=True)
+            fl = h.flags()
+            if fl.edge_overflow:
+                raise _lib.DiffPharError("edge buffer overflow persists after re-planning")
         if fl.nan_resets:
             print('Warning: detected nan, resetting EGNN output to zero.')
             h.reset_flags()

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 1
+#define DP_ABI_VERSION 2
 
 typedef enum dp_status {
     DP_OK = 0,
@@ -70,7 +70,8 @@ typedef struct dp_handle dp_handle;
  * (dynamics.py:129-131, en_diffusion.py:919-924, conditional_model.py:450-457). */
 typedef struct dp_flags {
     int32_t nan_resets;           /* denoiser calls whose velocity held a NaN (then zeroed) */
-    int32_t edge_overflow;        /* 1 if a graph build exceeded edge_capacity */
+    int32_t edge_overflow;        /* 0, or the edge count of a graph build that exceeded edge_capacity (the graph was
+                                     truncated to the capacity: results are invalid, re-plan with at least this many) */
     float max_mean_rel_err;       /* max over checked steps of |sum x| / (max|x| + 1e-10) */
     float last_max_cog;           /* max |sum_sample x_phar| after the final step */
     int64_t last_n_edges;         /* E of the most recent graph build */
@@ -141,6 +142,32 @@ int dp_sample(dp_handle* h, float* xh_pocket_dev, const float* noise_dev,
 /* Same through HOST buffers (H2D + D2H inside; what bench.py's e2e times). */
 int dp_sample_host(dp_handle* h, const float* xh_pocket_host, const float* noise_host,
                    float* out_phar_host, float* xh_pocket_out_host);
+
+/* Options of dp_sample_ex.  Replaces the rest of sample_given_pocket's loop body:
+ *   - noise_dev == NULL: the gaussian draws of sample_gaussian (en_diffusion.py:946-949) come from a counter-based
+ *     generator on the device (Philox4x32-10 + Box-Muller) keyed by `seed` and each sample's GLOBAL id, so the result
+ *     of a sample does not depend on how a pocket list is batched or sharded over GPUs;
+ *   - return_frames > 1: the intermediate states the reference saves every n_steps / return_frames steps
+ *     (conditional_model.py:439-442), un-normalised like unnormalize_z (en_diffusion.py:891-906), written from inside
+ *     the captured step; frame 0 is left for the caller to overwrite with the final result (conditional_model.py:459-460). */
+typedef struct dp_sample_opts {
+    const float* noise_dev;            /* [n_steps+2, N_p, 3+phar_nf] injected noise, or NULL */
+    uint64_t seed;                     /* used when noise_dev is NULL */
+    const int64_t* sample_ids_host;    /* [n_samples] global sample ids, or NULL: keep the current ones (0..n-1 after dp_plan) */
+    int32_t return_frames;             /* <= 1: final state only */
+    float norm_x, norm_h, bias_h;      /* norm_values[0], norm_values[1], norm_biases[1] */
+    float* frames_phar_dev;            /* [return_frames, N_p, 3+phar_nf] (return_frames > 1) */
+    float* frames_pocket_dev;          /* [return_frames, N_r, 3+residue_nf] */
+} dp_sample_opts;
+int dp_sample_ex(dp_handle* h, float* xh_pocket_dev, const dp_sample_opts* opts, float* out_phar_dev, void* stream);
+/* The same generator into a caller buffer [n_draws, N_p, 3+phar_nf] (parity tests feed it to the CPU oracle). */
+int dp_fill_noise(dp_handle* h, uint64_t seed, const int64_t* sample_ids_host, int32_t n_draws, float* noise_dev, void* stream);
+/* dp_sample_host without a noise upload: the draws are generated on the device. */
+int dp_sample_host_seeded(dp_handle* h, const float* xh_pocket_host, uint64_t seed, const int64_t* sample_ids_host,
+                          float* out_phar_host, float* xh_pocket_out_host);
+/* how many times the denoising-step CUDA graph was captured by this handle (it is re-captured only when the batch
+ * layout, the precision, the step count or the frame count changes) */
+int64_t dp_graph_captures(const dp_handle* h);
 
 int dp_get_flags(dp_handle* h, dp_flags* out, void* stream);
 int dp_reset_flags(dp_handle* h, void* stream);
