@@ -3,9 +3,9 @@ same output file — ``phar_to_coords_no_tensor_PI3K_dul.json`` in the CURRENT d
 the reference (``--outdir`` is parsed and unused there too) — and the same final ``print`` of the dict.
 
     python -m cmd_gen_b200.generate_phars <checkpoint> --pdbfile P.pdb --ref_ligand A:1101 \\
-        --n_samples 10 --num_nodes_phar 10 [--timesteps 100] [--precision bf16|f16|fp32]
+        --n_samples 10 --num_nodes_phar 10 [--timesteps 100] [--precision f16fast|f16|bf16|fp32]
 
-``--precision`` is the only addition (arithmetic mode of the CUDA kernels; default bf16 tensor-core tiles).
+``--precision`` is the only addition (arithmetic mode of the CUDA kernels; default f16fast: f16 tensor-core tiles, packed-f16 first layer).
 """
 import argparse
 import json

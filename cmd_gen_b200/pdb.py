@@ -108,7 +108,10 @@ def pocket_from_ligand(residues: List[Residue], ligand_id: str, dist_cutoff: flo
     lig_xyz = lig[0].coords().astype(np.float64)
     out = []
     for r in residues:
-        if r.hetero or r.resname not in THREE_TO_ONE:      # is_aa(resname, standard=True)
+        # is_aa(resname, standard=True) is the reference's only filter (utils.py:115): a standard amino acid written as
+        # HETATM (peptide ligands, some modified-chain exports) counts; its `residue.id[1] == resi` ligand skip compares
+        # an int with a str and never fires, so a ligand that is itself a standard amino acid is kept too
+        if r.resname not in THREE_TO_ONE:
             continue
         d = r.coords().astype(np.float64)[:, None, :] - lig_xyz[None, :, :]
         if np.sqrt((d * d).sum(-1)).min() < dist_cutoff:
