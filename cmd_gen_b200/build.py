@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libdiffphar_b200.so")
-SOURCES = ["api.cu", "graph.cu", "egnn_f32.cu", "small.cu", "tc_weights.cu", "tc_edge.cu", "tc_node.cu", "stats.cu"]
+SOURCES = ["api.cu", "graph.cu", "egnn_f32.cu", "small.cu", "tc_weights.cu", "tc_edge.cu", "tc_node.cu", "tc_tf32.cu", "stats.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -350,7 +350,7 @@ extern "C" int dp_set_weights(dp_handle* h, const float* blob, int64_t n_floats)
         for (float& b : bias_half) b *= 0.5f;
         if ((rc = upload(bag, &ps.b_half, bias_half))) return rc;
         HostLinear& TL = h->tc_host[4 * G + c.n_layers + v];
-        TL.K = H; TL.n_out = n_out; TL.wt = wt;
+        TL.K = H; TL.n_out = n_out; TL.wt = wt; TL.tf32_scale = 2.0f;
         for (float& w : TL.wt) w *= 0.5f;
     }
     if ((rc = tc_prepare_weights(h))) return rc;
@@ -547,8 +547,8 @@ extern "C" int dp_get_graph(dp_handle* h, const int32_t** rowptr, const int32_t*
 static int run_linear(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st)
 {
     prof_begin(h, PROF_NODE, st);
-    (void)lin_id;                                    // the tcgen05 path runs the fused node kernel instead (tc_node.cu)
-    int rc = launch_linear_f32(h, a, st);
+    // DP_TF32: the same per-node GEMMs on kind::tf32 tiles; the 16-bit modes run the fused node kernel instead (tc_node.cu)
+    int rc = h->precision == DP_TF32 ? launch_linear_tf32(h, a, lin_id, st) : launch_linear_f32(h, a, st);
     prof_end(h, st);
     return rc;
 }
@@ -557,7 +557,8 @@ static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st
 {
     if (h->skip_mask & (a.coord ? 4 : 1)) return DP_OK;
     prof_begin(h, a.coord ? PROF_EDGE_COORD : PROF_EDGE_MSG, st);
-    int rc = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
+    int rc = h->precision == DP_TF32 ? launch_edge_tf32(h, a, lin_id, st)
+             : (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
     prof_end(h, st);
     return rc;
 }
@@ -570,7 +571,8 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
 {
     Plan& p = h->plan; const dp_config& c = h->cfg; DeviceWeights& W = h->w;
     const int S = c.inv_sublayers, G = c.n_layers * S;
-    const int unit = (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? UNIT_F32 : UNIT_TC;
+    const bool fp32_layout = h->precision == DP_FP32 || h->precision == DP_TF32 || !(h->tc_mask & 1);   // fp32 pq, 64-edge units
+    const int unit = fp32_layout ? UNIT_F32 : UNIT_TC;
     int rc = 0;
     if (!(h->skip_mask & 32) && (rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
     // Fork: the radius graph (needs x only) runs on a side branch while the main branch projects the embedded
@@ -598,7 +600,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     av.src = unit == UNIT_TC ? p.agg_src : nullptr;
     av.norm = c.normalization_factor; av.inv_norm = 1.0f / c.normalization_factor; av.mean = c.aggregation_mean;
 
-    const bool fused_node = h->precision != DP_FP32 && (h->tc_mask & 2);
+    const bool fused_node = !fp32_layout && (h->tc_mask & 2);
     auto node_phase = [&](int v) -> int {      // tcgen05: node MLP of GCL v-1 + projection of the new h, one launch
         if (h->skip_mask & 2) return DP_OK;
         prof_begin(h, PROF_NODE, st);
@@ -644,11 +646,17 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
+            q.x_next = x_next; q.norm_constant = c.norm_constant; q.coords_range = c.coords_range;
+            q.norm_factor = c.normalization_factor; q.mean = c.aggregation_mean;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
-            prof_begin(h, PROF_EDGE_COORD, st);
-            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
-            prof_end(h, st);
-            if (rc) return rc;
+            // the tcgen05 kernel finishes its own phar rows (tc_edge.cu, coordinate mode); the FFMA path runs the stand-alone finish
+            const bool fused_finish = !fp32_layout && !(h->dbg & 8);
+            if (!fused_finish) {
+                prof_begin(h, PROF_EDGE_COORD, st);
+                rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
+                prof_end(h, st);
+                if (rc) return rc;
+            }
             float* t = x_cur; x_cur = x_next; x_next = t;
         }
     }

@@ -181,6 +181,7 @@ struct TcWeights;   // tcgen05 operand images (tc_weights.cu)
 struct HostLinear {  // k-major fp32 host copy of a linear the tensor-core path packs: wt[k * n_out + o]
     std::vector<float> wt;
     int K = 0, n_out = 0;
+    float tf32_scale = 1.f;   // the projections are registered pre-scaled by 1/2 for the 16-bit path; the tf32 image undoes it
 };
 
 // ---------------------------------------------------------------------------
@@ -335,6 +336,8 @@ struct EdgeArgs {
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)
+    float* x_next;                                   // coord == 1, tcgen05 path: the kernel finishes the phar rows itself (x + masked row sum)
+    float norm_constant, coords_range, norm_factor; int mean;   // ... with these (coord2diff, egnn_new.py:91, 283-291)
     int coord; int attention; int use_tanh;
     long long* trace;                                // debug timeline (dp_debug_trace), normally null
 };
@@ -375,6 +378,9 @@ int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)
 int tc_edge_init();
 int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st);                 // tc_node.cu
 int tc_node_init();
+int launch_linear_tf32(dp_handle* h, const LinearArgs& a, int lin_id, cudaStream_t st);     // tc_tf32.cu (DP_TF32)
+int launch_edge_tf32(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st);
+int tc_tf32_init();
 
 // api.cu helpers
 void prof_begin(dp_handle* h, int which, cudaStream_t st);

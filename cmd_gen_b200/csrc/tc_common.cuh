@@ -427,7 +427,11 @@ __device__ __forceinline__ uint32_t chunk_offset(int i, int chunk, int panel_byt
 }  // namespace tc
 
 // ---- weight images (tc_weights.cu) ----------------------------------------------------------------
-struct TcLinearImg { unsigned char* img[2] = {nullptr, nullptr}; int K = 0, n_out = 0; };
+struct TcLinearImg {
+    unsigned char* img[2] = {nullptr, nullptr};   // swizzled 16-bit panels (64 K per 128-byte row), per format
+    unsigned char* img_tf32 = nullptr;            // swizzled tf32 panels (32 K per 128-byte row), UN-scaled weights (tc_tf32.cu)
+    int K = 0, n_out = 0;
+};
 struct TcNodeImg {                     // concatenated panel stream of one fused node-phase launch
     unsigned char* img[2] = {nullptr, nullptr};
     int n_panels = 0;

@@ -59,7 +59,7 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
-constexpr int REGS_MMA = 32;
+constexpr int REGS_MMA = 40;                      // 32 spilled ~20 registers around the weight fill (tcgen05.cp descriptors); 40 is what the pool has left
 #ifndef EDGE_REGS_PACKED_PRODUCER
 #define EDGE_REGS_PACKED_PRODUCER 104
 #define EDGE_REGS_PACKED_EPILOGUE 64
@@ -135,11 +135,17 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     int s_row = 0, s_col = 0; float s_d0 = 0.f;
-    if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+    if (!a.coord && !a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
-    const int E = *a.n_edges;
+    // Coordinate mode: the CTA OWNS a contiguous range of phar rows [c_r0, c_r1) — hence a contiguous CSR edge range
+    // [c_e0, c_e1) — so that after its tiles it can finish those rows itself (coord_diff * scalar, row sum, x update:
+    // egnn_new.py:91-103) without any cross-CTA dependency: no second launch, no global round trip through another kernel.
+    const int c_r0 = a.coord ? (int)((long long)blockIdx.x * a.n_moving / (int)gridDim.x) : 0;
+    const int c_r1 = a.coord ? (int)((long long)(blockIdx.x + 1) * a.n_moving / (int)gridDim.x) : 0;
+    const int c_e0 = a.coord ? a.rowptr[c_r0] : 0, c_e1 = a.coord ? a.rowptr[c_r1] : 0;
+    const int E = a.coord ? c_e1 : *a.n_edges;               // exclusive end of the edges this CTA may touch
 
     // ---- prologue
     if (tid == 0) {
@@ -192,12 +198,16 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     // for every CTA that has a long lane and one (empty, skipped by has_unit) tile too many for the others — which
     // finish no later than the CTAs that need it.  Idle CTAs fall through with 0.
     int my_tiles;
-    if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
+    if (a.coord) my_tiles = (c_e1 - c_e0 + TILE - 1) / TILE;
+    else if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
     else my_tiles = max(0, ((E + TILE - 1) / TILE - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
-    // group g's unit of tile `it` is unit_base(g) + it * unit_step, and exists while it < unit_count(g)
-    const int unit_step = a.contig ? 1 : 4 * (int)gridDim.x;
-    auto unit_base = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
-    auto unit_count = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
+    // group g's 16 edges of tile `it` start at edge_base(g) + it * edge_step, and exist while it < unit_count(g)
+    //   coordinate mode: tiles are 64 consecutive edges from the CTA's first edge (any alignment: nothing is keyed on units)
+    const bool lanes = a.contig && !a.coord;
+    const int edge_step = a.coord ? TILE : (lanes ? UNIT_TC : TILE * (int)gridDim.x);
+    auto unit_base = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
+    auto edge_base = [&](int g) { return a.coord ? c_e0 + UNIT_TC * g : UNIT_TC * unit_base(g); };
+    auto unit_count = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
 
     if (wid >= MMA_WARP) {
         // ================================ MMA issuer ================================
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_producer(MODE)));
         const int pw = wid - EPI_WARPS;
-        const int unit0 = unit_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
+        const int ebase = edge_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
         const int e_off = 8 * (pw & 1) + lane;                                           // its half of the unit's 16 edges
         float wr[8], wd[8];
         unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         // Slots without an edge (past E, or past the end of a shorter lane) are processed as edge (0, 0): finite garbage in columns nobody reads.
         int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
         auto load_rc = [&](int it, int& r, int& c, float& d0) {
-            const int e = (unit0 + it * unit_step) * UNIT_TC + e_off;
+            const int e = ebase + it * edge_step + e_off;
             r = 0; c = 0; d0 = 0.f;
             if (it < n_units && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
         };
@@ -303,10 +313,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
         };
         int n_row, n_col; float n_d0;
-        if (a.contig) {
+        if (a.contig || a.coord) {
             load_rc(0, m_row, m_col, m_d0);
         } else {
-            const bool ok = my_tiles > 0 && lane < 8 && unit0 * UNIT_TC + e_off < E;       // the speculative loads were real edges
+            const bool ok = my_tiles > 0 && lane < 8 && ebase + e_off < E;                 // the speculative loads were real edges
             m_row = ok ? s_row : 0; m_col = ok ? s_col : 0; m_d0 = ok ? s_d0 : 0.f;
         }
         uint4 pb[8];
@@ -425,11 +435,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
         if (!a.tma_fill && my_tiles > 0) fill_weights();
-        const int unit0 = unit_base(gi), n_units = unit_count(gi);                      // this group's units
+        const int ebase = edge_base(gi), n_units = unit_count(gi);                      // this group's units
         float s0 = 0.f, s1 = 0.f;                                                        // running sum of the current CSR row: carried across tiles
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
-            const int u0 = (unit0 + it * unit_step) * UNIT_TC;                           // first edge of this group's unit
+            const int u0 = ebase + it * edge_step;                                       // first edge of this group's unit
             const bool has_unit = it < n_units;                                          // shorter lanes idle through the CTA's last tile
             const int my_dst = (!a.coord && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
@@ -520,6 +530,42 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 __syncwarp();                                                            // gatew / redw are rewritten next tile
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 7);
+        }
+        if (a.coord && !(a.dbg & 8)) {                                                   // dbg bit 3: A/B against the stand-alone finish launch
+            // ---- finish the CTA's own phar rows (replaces coord_finish_kernel): eight lanes per row, lane l takes the row's
+            // edges l, l + 8, ... in CSR order, a fixed-order shuffle tree combines them — deterministic, no atomics, the
+            // same arithmetic in the same order as the stand-alone kernel (small.cu) the FFMA path still launches.
+            named_bar_sync(1 + EPI_GROUPS, EPI_WARPS * 32);                              // every scalar of this CTA's rows is written
+            const int l = tid & 7;
+            for (int rb = c_r0; rb < c_r1; rb += EPI_WARPS * 4) {
+                const int r = rb + (tid >> 3);
+                const bool live = r < c_r1;
+                const int rs = live ? a.rowptr[r] : 0, re = live ? a.rowptr[r + 1] : 0;
+                const float xi = live ? a.x[3 * r] : 0.f, yi = live ? a.x[3 * r + 1] : 0.f, zi = live ? a.x[3 * r + 2] : 0.f;
+                float sx = 0.f, sy = 0.f, sz = 0.f;
+                for (int k = rs + l; k < re; k += 8) {
+                    const int j = a.ecol[k];
+                    const float dx = xi - a.x[3 * j], dy = yi - a.x[3 * j + 1], dz = zi - a.x[3 * j + 2];
+                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(r2, 1e-8f)), a.norm_constant);    // coord2diff, egnn_new.py:269-270
+                    const float v = a.escal[k];
+                    float tx = __fmul_rn(__fdiv_rn(dx, nrm), v), ty = __fmul_rn(__fdiv_rn(dy, nrm), v), tz = __fmul_rn(__fdiv_rn(dz, nrm), v);
+                    if (a.use_tanh) { tx = __fmul_rn(tx, a.coords_range); ty = __fmul_rn(ty, a.coords_range); tz = __fmul_rn(tz, a.coords_range); }
+                    sx = __fadd_rn(sx, tx); sy = __fadd_rn(sy, ty); sz = __fadd_rn(sz, tz);
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, o, 8));
+                    sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, sy, o, 8));
+                    sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, sz, o, 8));
+                }
+                if (live && l == 0) {
+                    const float d = a.mean ? (float)max(re - rs, 1) : a.norm_factor;             // egnn_new.py:283-291
+                    a.x_next[3 * r] = __fadd_rn(xi, __fdiv_rn(sx, d));
+                    a.x_next[3 * r + 1] = __fadd_rn(yi, __fdiv_rn(sy, d));
+                    a.x_next[3 * r + 2] = __fadd_rn(zi, __fdiv_rn(sz, d));
+                }
+            }
         }
     }
     tc_fence_before();

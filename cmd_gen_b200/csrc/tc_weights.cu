@@ -32,6 +32,7 @@ int tc_init()
 {
     int rc = tc_edge_init();
     if (!rc) rc = tc_node_init();
+    if (!rc) rc = tc_tf32_init();
     if (rc) return rc;
     return DP_OK;
 }
@@ -77,6 +78,27 @@ int tc_prepare_weights(dp_handle* h)
             T.lin[id].img[fmt] = reinterpret_cast<unsigned char*>(d);
         }
         T.lin[id].K = L.K; T.lin[id].n_out = L.n_out;
+        // tf32 image: 32 K elements per 128-byte row, values rounded to nearest (ties away, like cvt.rna.tf32.f32)
+        {
+            const int np32 = L.K / 32;
+            std::vector<uint32_t> img32((size_t)n_blocks * np32 * W_PANEL_BYTES / 4);
+            for (int o = 0; o < L.n_out; ++o) {
+                const int ob = o / 256, r = o % 256;
+                for (int k = 0; k < L.K; ++k) {
+                    const int kp = k / 32, kb = (k % 32) * 4;
+                    const size_t off = ((size_t)ob * np32 + kp) * W_PANEL_BYTES + (size_t)r * 128 + ((((kb >> 4) ^ (r & 7))) << 4) + (kb & 15);
+                    const float w = L.wt[(size_t)k * L.n_out + o] * L.tf32_scale;
+                    uint32_t u; memcpy(&u, &w, 4);
+                    if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+                    img32[off / 4] = u;
+                }
+            }
+            void* d = nullptr;
+            DP_CUDA(cudaMalloc(&d, img32.size() * 4));
+            T.allocations.push_back(d);
+            DP_CUDA(cudaMemcpy(d, img32.data(), img32.size() * 4, cudaMemcpyHostToDevice));
+            T.lin[id].img_tf32 = reinterpret_cast<unsigned char*>(d);
+        }
     }
     // Fused node-phase launches (tc_node.cu) stream ONE contiguous panel sequence: for h version v > 0 the
     // node MLP of GCL v-1 (node_mlp.0: 8 panels, node_mlp.2: 4 panels) followed by the projection blocks of
@@ -112,7 +134,6 @@ int tc_fmt_of(dp_handle* h, int* fmt)
 {
     if (h->precision == DP_BF16) { *fmt = FMT_BF16; return DP_OK; }
     if (h->precision == DP_F16 || h->precision == DP_F16_FAST || h->precision == DP_F16_FAST32) { *fmt = FMT_F16; return DP_OK; }
-    dp_set_error("precision mode %d: the tcgen05 kind::tf32 path (streamed fp32 weight tiles) is not built yet; "
-                 "use DP_FP32, DP_F16 (same 10-bit mantissa as TF32) or DP_BF16", h->precision);
+    dp_set_error("precision mode %d has no 16-bit operand format (DP_TF32 runs tc_tf32.cu, DP_FP32 egnn_f32.cu)", h->precision);
     return DP_ERR_INVALID;
 }

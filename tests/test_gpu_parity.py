@@ -160,11 +160,11 @@ def test_dynamics_fp32_vs_reference(name):
 
 # tensor-core modes: fp16 operands carry TF32's 10-bit mantissa, bf16 8 bits -> tighter bound for f16
 # "f16fast" = f16 operands with the edge kernels' first layer in packed f16x2 and tanh-form SiLU: between the two
-TC_TOL = {"f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
-TC_MODES = ("f16", "f16fast", "bf16")
+TC_TOL = {"tf32": (1e-4, 0.02), "f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
+TC_MODES = ("f16", "f16fast", "bf16")          # the 16-bit tcgen05 modes (tc_edge.cu / tc_node.cu); "tf32" runs tc_tf32.cu
 
 
-@pytest.mark.parametrize("prec", list(TC_MODES))
+@pytest.mark.parametrize("prec", ["tf32"] + list(TC_MODES))
 @pytest.mark.parametrize("name", CASES)
 def test_dynamics_tensor_core_modes_vs_reference(name, prec):
     g = load(f"dynamics_{name}.npz")
@@ -431,7 +431,7 @@ def inject(ddpm, noise):
     ddpm.sample_gaussian = lambda size, device: next(it).to(device)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16", "f16fast", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16", "f16fast", "bf16"])
 @pytest.mark.parametrize("fixture,name", [("sampler_ca_small_T500_n12.npz", "ca_small"),
                                           ("sampler_ca_small_T20.npz", "ca_small"),
                                           ("sampler_fa_small_T500_n6.npz", "fa_small")])
@@ -454,7 +454,7 @@ def test_sample_given_pocket_vs_reference(fixture, name, prec):
     err = np.abs(xh_phar.cpu().numpy()[:, :3] - g["xh_phar_f64"][:, :3]).max()
     # end-to-end bound: fp32 within 10x the reference's own fp32-vs-fp64 error (or 1e-4 of the scale);
     # f16 operands 3e-4, packed-f16 fast mode 4e-4, bf16 1e-3 of the coordinate scale
-    bound = {"fp32": max(10 * ref_err, 1e-4 * scale), "f16": 3e-4 * scale, "f16fast": 4e-4 * scale,
+    bound = {"fp32": max(10 * ref_err, 1e-4 * scale), "tf32": 3e-4 * scale, "f16": 3e-4 * scale, "f16fast": 4e-4 * scale,
              "bf16": 1e-3 * scale}[prec]
     assert err <= bound, (err, ref_err, scale)
     same = (xh_phar.cpu().numpy()[:, 3:] == g["xh_phar_f32"][:, 3:]).all(1).mean()

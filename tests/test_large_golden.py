@@ -13,12 +13,14 @@ precisions against the reference's fp64 outputs — not against the library's ow
 Stated tolerances (per denoiser call; `hs` = max |reference feature output|, `xs` = max |input coordinate|,
 `vs` = max |reference velocity|):
   fp32    : features 2e-5 hs, velocity 1e-5 xs           (the reference's own fp32-vs-fp64 error: 5e-8 / 2e-6)
-  f16     : features 1e-4 hs, velocity 1e-5 xs + 0.02 vs  ("TF32-class": 10-bit mantissa operands)
+  tf32    : features 1e-4 hs, velocity 1e-5 xs + 0.02 vs  (tcgen05 kind::tf32 tiles, fp32 storage: 10-bit mantissa operands)
+  f16     : features 1e-4 hs, velocity 1e-5 xs + 0.02 vs  (f16 operands: the same 10-bit mantissa, 16-bit storage of pq)
   f16fast : features 2e-4 hs, velocity 1e-5 xs + 0.03 vs
   bf16    : features 1e-3 hs, velocity 1e-5 xs + 0.05 vs
   (config 3 / 5: feature bounds x4 — ~40 messages per node and up to 9 blocks accumulate operand rounding)
 End to end after 500 steps (config 1, `scale` = max |final coordinate| = 1 097): fp32 max(10 x the reference's own
-fp32-vs-fp64 error, 1e-4 scale); f16 3e-4, f16fast 4e-4, bf16 1e-3 of scale; types identical (fp32) / >= 90 %.
+fp32-vs-fp64 error, 1e-4 scale); tf32 / f16 3e-4, f16fast 4e-4, bf16 1e-3 of scale; types identical (fp32) / >= 90 %.
+BASELINE config 5's "bf16 MLP tiles vs TF32 accuracy check": test_config5_bf16_tiles_vs_tf32_accuracy.
 """
 import os
 
@@ -32,9 +34,9 @@ from oracle import large_cases as lc
 from tests.helpers import GOLDEN, load, T
 
 DEV = "cuda:0"
-TC_TOL = {"f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
+TC_TOL = {"tf32": (1e-4, 0.02), "f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
 DEEP = {"config2": 1.0, "config3": 4.0, "config5": 4.0}
-PRECISIONS = ["fp32", "f16", "f16fast", "bf16"]
+PRECISIONS = ["fp32", "tf32", "f16", "f16fast", "bf16"]
 
 
 def _fixture(name):
@@ -182,7 +184,7 @@ def test_config1_all_500_steps_vs_reference(prec):
     d = lc.sampler_inputs("config1")
     assert np.allclose(lc.checksum(d["noise"]), g["noise_checksum"], rtol=0, atol=1e-6)
     cfg = d["cfg"]
-    bound_rel = {"fp32": None, "f16": 3e-4, "f16fast": 4e-4, "bf16": 1e-3}[prec]
+    bound_rel = {"fp32": None, "tf32": 3e-4, "f16": 3e-4, "f16fast": 4e-4, "bf16": 1e-3}[prec]
     ref = g["xh_phar_f64"]
     scale = float(np.abs(ref[:, :3]).max())
     ref_err = float(np.abs(g["xh_phar_f32"][:, :3] - ref[:, :3]).max())
@@ -220,3 +222,25 @@ def test_config1_all_500_steps_vs_reference(prec):
         b_x = max(10 * r_err, 1e-4 * zs) if prec == "fp32" else bound_rel * zs
         assert np.abs(gz[:, :3] - rz[:, :3]).max() <= b_x, (idx, prec)
         assert np.abs(gz[:, 3:] - 4.0 * rz[:, 3:]).max() <= (1e-4 if prec == "fp32" else 10 * bound_rel) * max(1.0, np.abs(4 * rz[:, 3:]).max())
+
+
+@pytest.mark.gpu
+def test_config5_bf16_tiles_vs_tf32_accuracy():
+    """BASELINE configs[4]: 4k-node pockets, 12 phar points, 9 blocks — the bf16 MLP tiles against the TF32 tiles, both
+    measured against the reference's fp64 output: TF32 (and f16, the same mantissa) must be the more accurate."""
+    g, d = _dynamics_case("config5")
+    cfg = d["cfg"]
+    B = len(d["sizes"])
+    rp = g["eps_phar_f64_0"]
+    hs = max(1.0, float(np.abs(rp[:, 3:]).max()))
+    err = {}
+    for prec in ("tf32", "f16", "bf16"):
+        h = _handle(cfg, d["wseed"], prec)
+        h.plan(d["counts"], d["sizes"])
+        out_p, out_r = h.dynamics_forward(d["z"], d["xh_pocket"], torch.full((B,), float(g["t_values"][0])))
+        e_p = float(np.abs(out_p.cpu().numpy()[:, 3:] - rp[:, 3:]).max()) / hs
+        e_r = float(np.abs(out_r.cpu().numpy()[:, 3:] - g["eps_res_f64as32_0"]).max()) / max(1.0, float(g["eps_res_absmax_0"]))
+        err[prec] = max(e_p, e_r)
+    print(f"\n[parity] config5 accuracy vs reference fp64 (max feature error / max |ref|): {err}")
+    assert err["tf32"] < err["bf16"] and err["f16"] < err["bf16"]
+    assert err["tf32"] <= 4e-4 and err["bf16"] <= 4e-3
