@@ -147,7 +147,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
-    if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : 0;
+    if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "scan3") ? 3 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
             h->trace_kernel = atoi(m);
@@ -438,6 +438,8 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     // bucketed cell list: pays off once a sample has more nodes than a handful of warp sweeps (full-atom pockets)
     p.use_cells = c.edge_cutoff > 0.f && p.max_nodes <= CELL_SAMPLE_MAX_NODES &&
                   (h->graph_mode == 2 || (h->graph_mode == 0 && p.max_nodes >= 512));
+    // one-launch scan builder: a sample's candidates must fit 32 ballot chunks (two ranges, each rounded up to 32)
+    p.fused_graph = !p.use_cells && !p.seg_lanes && h->graph_mode != 3 && p.max_nodes <= 960;
     // One arena for every per-plan buffer: a layout that fits the arena re-carves it (no cudaMalloc / cudaFree, each of
     // which synchronises the device), so walking a pocket list re-plans in microseconds.
     Carver cv;
@@ -445,6 +447,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.deg, p.N); cv.take(&p.rowptr, p.N + 1); cv.take(&p.agg_src, p.N);
     cv.take(&p.col, ecap); cv.take(&p.erow, ecap); cv.take(&p.edst, ecap); cv.take(&p.d0, ecap); cv.take(&p.escal, ecap);
     cv.take(&p.counts, 4);
+    cv.take(&p.scan_status, (size_t)p.N / 64 + 2);
     if (p.use_cells) {
         cv.take(&p.cell_start, (size_t)B * (CELLS_MAX + 1)); cv.take(&p.cell_nodes, p.N); cv.take(&p.cell_grid, (size_t)B * 8);
         p.bitmap_words = (p.max_nodes + 31) / 32;

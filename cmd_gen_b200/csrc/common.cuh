@@ -215,6 +215,8 @@ struct Plan {
     float* cell_grid = nullptr;  // [B][8]: origin xyz, inverse cell size xyz, dims packed (nx | ny << 8 | nz << 16) as int bits
     unsigned* row_bitmap = nullptr;  // [N][bitmap_words]: per-row hit bitmap over the sample's nodes, count pass -> fill pass
     int bitmap_words = 0;        // ceil(max nodes per sample / 32)
+    int fused_graph = 0;         // one-launch scan builder (graph.cu radius_rows_fused_kernel): small samples, units scheme
+    unsigned long long* scan_status = nullptr;   // [ceil(N / 64)] look-back status words of that kernel
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
@@ -262,7 +264,8 @@ struct dp_handle {
     int tma_fill = 1;                  // DIFFPHAR_TMA_FILL=0: resident weights through LDG + tcgen05.st (A/B; EdgeArgs::tma_fill)
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
-    int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells
+    int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells,
+                                       // 3 = the three-launch scan (A/B of the one-launch builder)
     int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
     DeviceWeights w;

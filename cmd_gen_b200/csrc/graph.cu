@@ -30,6 +30,7 @@ struct GraphArgs {
     long long ecap;
     int* cell_start; int* cell_nodes; float* cell_grid;
     unsigned* row_bitmap; int bitmap_words;          // cells builder: the count pass keeps each row's hit bitmap for the fill pass
+    unsigned long long* status;                      // fused builder: per-CTA scan status words (decoupled look-back), zeroed per build
 };
 
 __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float xj, float yj, float zj)
@@ -116,6 +117,150 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
             }
         }
         if (!FILL && lane == 0) a.deg[row] = found;
+    }
+}
+
+// ---- one-launch builder for small samples (Calpha pockets) ----------------------------------------
+// count -> scan -> fill in ONE kernel: the three-launch version costs ~29 us at config-2 size (N = 10 k, 158 nodes per
+// sample), almost all of it launch latency and the single-CTA scan, and only ~10 us of it hide beside the first
+// projection.  Here a CTA owns 64 consecutive rows (8 warps x 8 rows):
+//   A  every warp sweeps its rows' samples once and keeps the 32-candidate ballots in registers (lane c = chunk c:
+//      a sample of < ~960 nodes has at most 32 chunks), degrees go to shared memory;
+//   B  warp 0 scans the 64 degrees and obtains the CTA's base offset by decoupled look-back over per-CTA status words
+//      (aggregate published at once, inclusive prefix as soon as the predecessors' are known; 32 predecessors per
+//      round trip) — CTAs are dispatched in index order and never wait for a later one;
+//   C  the fill replays the kept ballots: no second distance sweep, only d0 of the hits is recomputed.
+// Units scheme of the segmented sum only (edge_dst / agg_src need no global edge count there); identical output.
+constexpr int FUSED_ROWS = 64;
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_VAL = (1ull << 40) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) radius_rows_fused_kernel(GraphArgs a)
+{
+    __shared__ int degs[FUSED_ROWS];
+    __shared__ int excl[FUSED_ROWS];
+    __shared__ long long base_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int row0 = blockIdx.x * FUSED_ROWS;
+    pdl_launch_dependents();
+    pdl_wait();
+    // ---- A: one sweep per row, ballots kept
+    unsigned masks[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = row0 + wid * 8 + i;
+        masks[i] = 0u;
+        int found = 0;
+        if (row < a.N) {
+            const int b = a.sample_of[row];
+            const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
+            const int lo[2] = {a.phar_off[b], a.Np + a.res_off[b]};
+            const int hi[2] = {a.phar_off[b + 1], a.Np + a.res_off[b + 1]};
+            int chunk = 0;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
+                    const int j = j0 + lane;
+                    bool hit = false;
+                    if (j < hi[part]) {
+                        const float d2 = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                        hit = (a.cutoff < 0.f) || (__fsqrt_rn(d2) <= a.cutoff);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (lane == chunk) masks[i] = m;
+                    found += __popc(m);
+                }
+            }
+        }
+        if (lane == 0) degs[wid * 8 + i] = found;
+    }
+    __syncthreads();
+    // ---- B: CTA scan + decoupled look-back
+    if (wid == 0) {
+        const int v0 = degs[2 * lane], v1 = degs[2 * lane + 1];
+        int incl = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        excl[2 * lane] = incl - v0 - v1;
+        excl[2 * lane + 1] = incl - v1;
+        const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long prefix = 0ull;
+        if (blockIdx.x > 0) {
+            if (lane == 0) st_release_u64(a.status + blockIdx.x, ST_AGG | total);
+            for (int j = (int)blockIdx.x - 1;; j -= 32) {
+                const int idx = j - lane;
+                unsigned long long v = ST_INCL;                                  // before CTA 0: inclusive prefix 0
+                if (idx >= 0) { do { v = ld_acquire_u64(a.status + idx); } while (v == 0ull); }
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;          // nearest predecessor whose inclusive prefix is known
+                unsigned long long c = lane <= first ? (v & ST_VAL) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                prefix += c;
+                if (incl_mask) break;
+            }
+        }
+        if (lane == 0) {
+            st_release_u64(a.status + blockIdx.x, ST_INCL | (prefix + total));
+            base_s = (long long)prefix;
+            if (blockIdx.x == gridDim.x - 1) {                                   // the edge count: published clamped, see scan_rowptr_kernel
+                const long long E = (long long)(prefix + total);
+                const int Ec = (int)(E < a.ecap ? E : a.ecap);
+                const_cast<int*>(a.rowptr)[a.N] = Ec;
+                a.counts[0] = Ec;
+                if (a.Np >= a.N) a.counts[1] = Ec;
+                if (E > a.ecap && (int)E > a.counts[2]) a.counts[2] = (int)E;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- C: fill from the kept ballots
+    const long long cta_base = base_s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = row0 + wid * 8 + i;
+        if (row >= a.N) continue;
+        const long long base = cta_base + excl[wid * 8 + i];
+        const long long row_end = base + degs[wid * 8 + i];
+        const RowSeg seg = row_seg(a.N, base, row_end, 0, 0);
+        if (lane == 0) {
+            a.agg_src[row] = row_agg_src(seg, row, base, row_end);
+            const int bc = (int)(base < a.ecap ? base : a.ecap);
+            const_cast<int*>(a.rowptr)[row] = bc;
+            if (row == a.Np) a.counts[1] = bc;                                   // E_p: rows [0, Np) are the phar nodes
+        }
+        const int b = a.sample_of[row];
+        const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
+        const int lo[2] = {a.phar_off[b], a.Np + a.res_off[b]};
+        const int hi[2] = {a.phar_off[b + 1], a.Np + a.res_off[b + 1]};
+        int chunk = 0, found = 0;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
+                const unsigned m = __shfl_sync(0xffffffffu, masks[i], chunk);
+                if ((m >> lane) & 1u) {
+                    const int j = j0 + lane;
+                    const long long pos = base + found + __popc(m & ((1u << lane) - 1u));
+                    if (pos < a.ecap) {
+                        a.col[pos] = j;
+                        a.erow[pos] = row;
+                        a.d0[pos] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                        a.edst[pos] = edge_dst(seg, row, base, row_end, pos);
+                    }
+                }
+                found += __popc(m);
+            }
+        }
     }
 }
 
@@ -389,6 +534,7 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     a.counts = p.counts; a.ecap = p.Ecap;
     a.cell_start = p.cell_start; a.cell_nodes = p.cell_nodes; a.cell_grid = p.cell_grid;
     a.row_bitmap = p.row_bitmap; a.bitmap_words = p.bitmap_words;
+    a.status = p.scan_status;
     const int wpb = 8;
     int grid = (p.N + wpb - 1) / wpb;
     const int max_grid = h->sm_count * 16;
@@ -407,6 +553,12 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
         DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
         DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<true>, dim3(grid), dim3(256), 0, st, a));
         h->launches += 1;
+    } else if (p.fused_graph) {
+        // one launch (+ the status clear): see radius_rows_fused_kernel
+        const int n_cta = (p.N + FUSED_ROWS - 1) / FUSED_ROWS;
+        DP_CUDA(cudaMemsetAsync(p.scan_status, 0, (size_t)n_cta * sizeof(unsigned long long), st));
+        DP_CUDA(launch_kernel(h->pdl, radius_rows_fused_kernel, dim3(n_cta), dim3(256), 0, st, a));
+        h->launches -= 2;
     } else {
         DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));
         DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));

@@ -145,8 +145,128 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
     def sample(self, *args):
         raise NotImplementedError("Conditional model does not support sampling without given pocket.")
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("training losses are outside the accelerated sampling path")
+    # ---------------------------------------------------------------- loss terms (forward values only)
+    # conditional_model.py:20-106, 158-320 and en_diffusion.py:167-179, 834-848, 908-944.  The denoiser evaluation —
+    # the only expensive part — runs through the C-ABI (one dp_dynamics_forward with a per-sample t); everything
+    # else is the reference's [B]-sized torch arithmetic.  VALUES ONLY: there is no backward through the CUDA kernels,
+    # so this serves validation / test NLL (lightning_modules.py:264-287) and loss monitoring, not optimisation.
+    def subspace_dimensionality(self, input_size):
+        return (input_size - 1) * self.n_dims
+
+    def delta_log_px(self, num_nodes):
+        import numpy as np
+        return -self.subspace_dimensionality(num_nodes) * np.log(self.norm_values[0])
+
+    def log_pN(self, N_phar, N_pocket):
+        return self.size_distribution.log_prob_n1_given_n2(N_phar, N_pocket)
+
+    @staticmethod
+    def sum_except_batch(x, indices):
+        return scatter_add(x.sum(-1), indices)
+
+    @staticmethod
+    def cdf_standard_gaussian(x):
+        import math
+        return 0.5 * (1. + torch.erf(x / math.sqrt(2)))
+
+    @staticmethod
+    def gaussian_KL(q_mu_minus_p_mu_squared, q_sigma, p_sigma, d):
+        return d * torch.log(p_sigma / q_sigma) + 0.5 * (d * q_sigma ** 2 + q_mu_minus_p_mu_squared) / (p_sigma ** 2) - 0.5 * d
+
+    def sample_timesteps(self, lowest_t, n, device):
+        """t ~ U{lowest_t..T} per sample (conditional_model.py:212-214); a hook like sample_gaussian for the parity harness."""
+        return torch.randint(lowest_t, self.T + 1, size=(n, 1), device=device).float()
+
+    def kl_prior(self, xh_phar, mask_phar, num_nodes):
+        batch_size = len(num_nodes)
+        ones = torch.ones((batch_size, 1), device=xh_phar.device)
+        gamma_T = self.gamma(ones)
+        alpha_T = self.alpha(gamma_T, xh_phar)
+        mu_T = alpha_T[mask_phar] * xh_phar
+        mu_T_x, mu_T_h = mu_T[:, :self.n_dims], mu_T[:, self.n_dims:]
+        sigma_T_x = self.sigma(gamma_T, mu_T_x).squeeze()
+        sigma_T_h = self.sigma(gamma_T, mu_T_h).squeeze()
+        kl_h = self.gaussian_KL(self.sum_except_batch(mu_T_h ** 2, mask_phar), sigma_T_h, torch.ones_like(sigma_T_h), d=1)
+        kl_x = self.gaussian_KL(self.sum_except_batch(mu_T_x ** 2, mask_phar), sigma_T_x, torch.ones_like(sigma_T_x),
+                                self.subspace_dimensionality(num_nodes))
+        return kl_x + kl_h
+
+    def log_constants_p_x_given_z0(self, n_nodes, device):
+        import numpy as np
+        batch_size = len(n_nodes)
+        gamma_0 = self.gamma(torch.zeros((batch_size, 1), device=device))
+        log_sigma_x = 0.5 * gamma_0.view(batch_size)
+        return self.subspace_dimensionality(n_nodes) * (-log_sigma_x - 0.5 * np.log(2 * np.pi))
+
+    def log_pxh_given_z0_without_constants(self, phar, z_0_phar, eps_phar, net_out_phar, gamma_0, epsilon=1e-10):
+        nd = self.n_dims
+        z_h = z_0_phar[:, nd:]
+        sigma_0_cat = self.sigma(gamma_0, target_tensor=z_0_phar) * self.norm_values[1]
+        log_px = -0.5 * self.sum_except_batch((eps_phar[:, :nd] - net_out_phar[:, :nd]) ** 2, phar['mask'])
+        onehot = phar['one_hot'] * self.norm_values[1] + self.norm_biases[1]
+        centered = z_h * self.norm_values[1] + self.norm_biases[1] - 1
+        log_ph_cat = torch.log(self.cdf_standard_gaussian((centered + 0.5) / sigma_0_cat[phar['mask']])
+                               - self.cdf_standard_gaussian((centered - 0.5) / sigma_0_cat[phar['mask']]) + epsilon)
+        log_prob = log_ph_cat - torch.logsumexp(log_ph_cat, dim=1, keepdim=True)
+        return log_px, self.sum_except_batch(log_prob * onehot, phar['mask'])
+
+    def noised_representation(self, xh_phar, xh0_pocket, phar_mask, pocket_mask, gamma_t):
+        nd = self.n_dims
+        alpha_t, sigma_t = self.alpha(gamma_t, xh_phar), self.sigma(gamma_t, xh_phar)
+        eps = self.sample_gaussian(size=(len(phar_mask), nd + self.phar_nf), device=phar_mask.device)
+        z_t = alpha_t[phar_mask] * xh_phar + sigma_t[phar_mask] * eps
+        xh_pocket = xh0_pocket.detach().clone()
+        z_t[:, :nd], xh_pocket[:, :nd] = self.remove_mean_batch(z_t[:, :nd], xh_pocket[:, :nd], phar_mask, pocket_mask)
+        return z_t, xh_pocket, eps
+
+    def xh_given_zt_and_epsilon(self, z_t, epsilon, gamma_t, batch_mask):
+        alpha_t, sigma_t = self.alpha(gamma_t, z_t), self.sigma(gamma_t, z_t)
+        return z_t / alpha_t[batch_mask] - epsilon * sigma_t[batch_mask] / alpha_t[batch_mask]
+
+    @torch.no_grad()
+    def forward(self, phar, pocket, return_info=False):
+        """The loss / NLL terms of one batch (conditional_model.py:198-320), same tuple, forward values only."""
+        nd = self.n_dims
+        phar, pocket = self.normalize(phar, pocket)
+        delta_log_px = self.delta_log_px(phar['size'])
+        lowest_t = 0 if self.training else 1
+        t_int = self.sample_timesteps(lowest_t, phar['size'].size(0), phar['x'].device)
+        s_int = t_int - 1
+        t_is_zero = (t_int == 0).float()
+        t_is_not_zero = 1 - t_is_zero
+        s, t = s_int / self.T, t_int / self.T
+        gamma_s = self.inflate_batch_array(self.gamma(s), phar['x'])
+        gamma_t = self.inflate_batch_array(self.gamma(t), phar['x'])
+        xh0_phar = torch.cat([phar['x'], phar['one_hot']], dim=1)
+        xh0_pocket = torch.cat([pocket['x'], pocket['one_hot']], dim=1)
+        xh0_phar[:, :nd], xh0_pocket[:, :nd] = self.remove_mean_batch(xh0_phar[:, :nd], xh0_pocket[:, :nd],
+                                                                     phar['mask'], pocket['mask'])
+        z_t, xh_pocket, eps_t = self.noised_representation(xh0_phar, xh0_pocket, phar['mask'], pocket['mask'], gamma_t)
+        net_out, _ = self.dynamics(z_t, xh_pocket, t, phar['mask'], pocket['mask'])
+        xh_phar_hat = self.xh_given_zt_and_epsilon(z_t, net_out, gamma_t, phar['mask'])
+        error_t = self.sum_except_batch((eps_t - net_out) ** 2, phar['mask'])
+        SNR_weight = (1 - self.SNR(gamma_s - gamma_t)).squeeze(1)
+        assert error_t.size() == SNR_weight.size()
+        neg_log_constants = -self.log_constants_p_x_given_z0(n_nodes=phar['size'], device=error_t.device)
+        kl_prior = self.kl_prior(xh0_phar, phar['mask'], phar['size'])
+        if self.training:
+            log_px, log_ph = self.log_pxh_given_z0_without_constants(phar, z_t, eps_t, net_out, gamma_t)
+            loss_0_x = -log_px * t_is_zero.squeeze()
+            loss_0_h = -log_ph * t_is_zero.squeeze()
+            error_t = error_t * t_is_not_zero.squeeze()
+        else:
+            t_zeros = torch.zeros_like(s)
+            gamma_0 = self.inflate_batch_array(self.gamma(t_zeros), phar['x'])
+            z_0, xh_pocket, eps_0 = self.noised_representation(xh0_phar, xh0_pocket, phar['mask'], pocket['mask'], gamma_0)
+            net_out_0, _ = self.dynamics(z_0, xh_pocket, t_zeros, phar['mask'], pocket['mask'])
+            log_px, log_ph = self.log_pxh_given_z0_without_constants(phar, z_0, eps_0, net_out_0, gamma_0)
+            loss_0_x, loss_0_h = -log_px, -log_ph
+        log_pN = self.log_pN(phar['size'], pocket['size'])
+        info = {'eps_hat_phar_x': scatter_mean(net_out[:, :nd].abs().mean(1), phar['mask']).mean(),
+                'eps_hat_phar_h': scatter_mean(net_out[:, nd:].abs().mean(1), phar['mask']).mean()}
+        loss_terms = (delta_log_px, error_t, torch.tensor(0.0), SNR_weight, loss_0_x, torch.tensor(0.0), loss_0_h,
+                      neg_log_constants, kl_prior, log_pN, t_int.squeeze(), xh_phar_hat)
+        return (*loss_terms, info) if return_info else loss_terms
 
     def sample_normal_zero_com(self, mu_phar, xh0_pocket, sigma, phar_mask, pocket_mask, fix_noise=False):
         if fix_noise:

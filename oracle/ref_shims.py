@@ -73,7 +73,7 @@ def load_reference():
 
 
 def build_reference_model(cfg, state, T=500, noise_schedule="polynomial_2", precision=1e-5,
-                          norm_values=(1.0, 4.0), dtype=torch.float32):
+                          norm_values=(1.0, 4.0), dtype=torch.float32, size_histogram=None):
     """Instantiate reference EGNNDynamics + ConditionalDDPM with OUR weights."""
     import contextlib
     import io
@@ -91,7 +91,7 @@ def build_reference_model(cfg, state, T=500, noise_schedule="polynomial_2", prec
         dyn.load_state_dict({k: v.clone() for k, v in state.items()}, strict=True)
         ddpm = ConditionalDDPM(
             dynamics=dyn, phar_nf=cfg.phar_nf, residue_nf=cfg.residue_nf, n_dims=cfg.n_dims,
-            size_histogram=[[1.0, 1.0], [1.0, 1.0]], timesteps=T, parametrization="eps",
+            size_histogram=[[1.0, 1.0], [1.0, 1.0]] if size_histogram is None else size_histogram, timesteps=T, parametrization="eps",
             noise_schedule=noise_schedule, noise_precision=precision, loss_type="l2",
             norm_values=norm_values, norm_biases=(None, 0.0))
     if dtype == torch.float64:

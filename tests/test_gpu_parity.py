@@ -747,3 +747,37 @@ def test_num_nodes_phar_none_draws_sizes_from_the_histogram(tmp_path):
     assert all(per_slot[f"Molecule_{k}"] == n9 for k in range(6, 10)) and 0 < n9 <= 12
     sizes = model.ddpm.size_distribution.sample_conditional(n1=None, n2=torch.full((400,), 40))
     assert set(sizes.tolist()) == {5, 9} and 0.6 < float((sizes == 9).float().mean()) < 0.9
+
+
+# ----------------------------------------------------------------------------- §8 f4: loss / NLL terms (forward values)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_loss_terms_vs_reference(mode):
+    """ConditionalDDPM.forward (conditional_model.py:198-320) through the mirror — the denoiser evaluations on the CUDA
+    path with a per-sample t, everything else the reference's batch-sized arithmetic — against the terms the
+    unmodified reference produced with the same injected timesteps and noise (oracle/make_golden_losses.py)."""
+    g = load("losses_ca_small.npz")
+    cfg = DynamicsConfig()
+    ddpm = build_ddpm(cfg, int(g["wseed"]), 500)
+    from cmd_gen_b200.equivariant_diffusion.en_diffusion import DistributionNodes
+    ddpm.size_distribution = DistributionNodes(np.ones((16, 64)))
+    ddpm.train(mode == "train")
+    inject(ddpm, T(g["noise"]))
+    ddpm.sample_timesteps = lambda lowest, n, device: T(g[f"t_{mode}"]).to(device)
+    counts = T(g["counts"])
+    B = counts.numel()
+    phar = {"x": T(g["phar_x"]).to(DEV), "one_hot": torch.nn.functional.one_hot(T(g["phar_types"]), cfg.phar_nf).float().to(DEV),
+            "size": counts.to(DEV), "mask": torch.repeat_interleave(torch.arange(B), counts).to(DEV)}
+    pocket = {"x": T(g["pocket_x"]).to(DEV), "one_hot": T(g["pocket_one_hot"]).float().to(DEV),
+              "size": T(g["sizes"]).to(DEV), "mask": T(g["pocket_mask"]).to(DEV)}
+    res = ddpm(phar, pocket, return_info=True)
+    names = ["delta_log_px", "error_t_phar", "error_t_pocket", "SNR_weight", "loss_0_x_phar", "loss_0_x_pocket", "loss_0_h",
+             "neg_log_constants", "kl_prior", "log_pN", "t_int", "xh_phar_hat"]
+    for name, v in zip(names, res[:-1]):
+        ref = g[f"{mode}_f64_{name}"]
+        got = v.detach().cpu().double().numpy() if torch.is_tensor(v) else np.asarray(v, dtype=np.float64)
+        ref32 = g[f"{mode}_f32_{name}"]
+        tol = max(10 * float(np.abs(ref32 - ref).max()), 2e-5 * max(1.0, float(np.abs(ref).max())))
+        assert got.shape == ref.shape, name
+        assert np.abs(got - ref).max() <= tol, (name, np.abs(got - ref).max(), tol)
+    for k in ("eps_hat_phar_x", "eps_hat_phar_h"):
+        assert abs(float(res[-1][k]) - float(g[f"{mode}_f64_info_{k}"])) <= 2e-5 * max(1.0, abs(float(g[f"{mode}_f64_info_{k}"])))
