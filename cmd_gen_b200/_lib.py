@@ -35,7 +35,8 @@ class DpConfig(C.Structure):
 
 class DpFlags(C.Structure):
     _fields_ = [("nan_resets", C.c_int32), ("edge_overflow", C.c_int32), ("max_mean_rel_err", C.c_float),
-                ("last_max_cog", C.c_float), ("last_n_edges", C.c_int64), ("last_n_edges_phar", C.c_int64)]
+                ("last_max_cog", C.c_float), ("last_n_edges", C.c_int64), ("last_n_edges_phar", C.c_int64),
+                ("f16_range", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DpSampleOpts(C.Structure):

@@ -459,7 +459,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.x_in, (size_t)p.N * 3); cv.take(&p.x_a, (size_t)p.N * 3); cv.take(&p.x_b, (size_t)p.N * 3);
     cv.take(&p.z, (size_t)p.Np * PW); cv.take(&p.eps_hat, (size_t)p.Np * PW); cv.take(&p.pocket, (size_t)p.Nr * RW);
     cv.take(&p.out_buf, (size_t)p.Np * PW);
-    cv.take(&p.t_const, 4); cv.take(&p.step_idx, 1); cv.take(&p.nan_flag, 2);
+    cv.take(&p.t_const, 4); cv.take(&p.step_idx, 1); cv.take(&p.nan_flag, 4);
     int rc = h->arena.reserve(cv.total);
     if (rc) return rc;
     cv.assign(h->arena.p);
@@ -469,7 +469,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     DP_CUDA(cudaMemcpy(p.sample_of, sample_of.data(), (size_t)p.N * sizeof(int), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(p.sample_ids, ids.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemset(p.counts, 0, 4 * sizeof(int)));
-    DP_CUDA(cudaMemset(p.nan_flag, 0, 2 * sizeof(int)));
+    DP_CUDA(cudaMemset(p.nan_flag, 0, 4 * sizeof(int)));
     DP_CUDA(cudaMemset(p.step_idx, 0, sizeof(int)));
     DP_CUDA(cudaMemset(p.t_const, 0, 4 * sizeof(float)));
     h->has_plan = true;
@@ -623,6 +623,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.tma_fill = h->tma_fill; e.dbg = h->dbg; e.contig = p.seg_lanes;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
         e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
+        e.range_flag = p.nan_flag + 2;
         if ((rc = run_edge(h, e, 4 * i + 0, st))) return rc;
         // node model: h <- h + W4 silu(W3 [h | agg] + b3) + b4  (egnn_new.py:54-57)
         if (fused_node) {
@@ -648,7 +649,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
             q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
-            q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr;
+            q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr; q.range_flag = p.nan_flag + 2;
             q.x_next = x_next; q.norm_constant = c.norm_constant; q.coords_range = c.coords_range;
             q.norm_factor = c.normalization_factor; q.mean = c.aggregation_mean;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
@@ -919,7 +920,7 @@ extern "C" int dp_get_flags(dp_handle* h, dp_flags* out, void* stream)
     DP_CHECK(out, DP_ERR_INVALID, "dp_get_flags: null out");
     Plan& p = h->plan;
     cudaStream_t st = (cudaStream_t)stream;
-    int counts[4], nan[2];
+    int counts[4], nan[4];
     DP_CUDA(cudaMemcpyAsync(counts, p.counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
     DP_CUDA(cudaMemcpyAsync(nan, p.nan_flag, sizeof(nan), cudaMemcpyDeviceToHost, st));
     std::vector<float> stats((size_t)p.stats_cap * 2, 0.f);
@@ -927,6 +928,7 @@ extern "C" int dp_get_flags(dp_handle* h, dp_flags* out, void* stream)
     DP_CUDA(cudaStreamSynchronize(st));
     memset(out, 0, sizeof(*out));
     out->nan_resets = nan[1];
+    out->f16_range = nan[2];
     out->edge_overflow = counts[2];
     out->last_n_edges = counts[0];
     out->last_n_edges_phar = counts[1];
@@ -947,7 +949,7 @@ extern "C" int dp_reset_flags(dp_handle* h, void* stream)
     Plan& p = h->plan;
     cudaStream_t st = (cudaStream_t)stream;
     DP_CUDA(cudaMemsetAsync(p.counts + 2, 0, sizeof(int), st));
-    DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, 2 * sizeof(int), st));
+    DP_CUDA(cudaMemsetAsync(p.nan_flag, 0, 4 * sizeof(int), st));
     if (p.stats) DP_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.stats_cap * 2 * sizeof(float), st));
     return DP_OK;
 }

@@ -237,7 +237,8 @@ struct Plan {
     float* step_rows = nullptr;  // [n_steps][4]   (handle-owned: dp_handle::steps)
     float* stats = nullptr;      // [n_steps+2][2] (max |sum x|, max |x|) as float bits (handle-owned)
     int stats_cap = 0;
-    int* nan_flag = nullptr;     // [2]: current-call flag, sticky count
+    int* nan_flag = nullptr;     // [4]: current-call NaN flag, sticky NaN count, sticky f16-range bits (1: |pq| beyond what f16 adds
+                                 // safely, 2: r2 / d0 clamped to 60 000 by the packed-f16 first layer), spare
     int64_t* sample_ids = nullptr;   // [B] global id of each sample: selects its counter-based noise stream (small.cu)
     float* out_buf = nullptr;    // [Np][3+P] dp_sample_host staging
     // layout as planned (host copies: an identical dp_plan call keeps the captured graph)
@@ -343,6 +344,7 @@ struct EdgeArgs {
     float norm_constant, coords_range, norm_factor; int mean;   // ... with these (coord2diff, egnn_new.py:91, 283-291)
     int coord; int attention; int use_tanh;
     long long* trace;                                // debug timeline (dp_debug_trace), normally null
+    int* range_flag;                                 // tcgen05 path: sticky f16-range bits (Plan::nan_flag + 2)
 };
 int launch_edge_f32(dp_handle* h, const EdgeArgs& a, cudaStream_t st);
 int egnn_f32_init();

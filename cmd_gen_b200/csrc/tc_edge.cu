@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             if (PACKED) {                                                               // (r2, d0) of the lane's edge as one f16x2 word
                 const __half2 t = __floats2half2_rn(fminf(m_r2, 60000.f), fminf(m_d0, 60000.f));
                 m_rd = *reinterpret_cast<const uint32_t*>(&t);
+                // beyond f16's range the clamp makes this edge differ from the reference (only reachable without a cutoff):
+                // flagged, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
+                if (fmaxf(m_r2, m_d0) > 60000.f) atomicOr(a.range_flag, 2);
             }
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll

@@ -61,6 +61,7 @@ struct NodeArgs {
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
     int dbg;                                     // timing experiments (DIFFPHAR_DBG), 0 in production
     int fast_silu;                               // SiLU in the one-MUFU tanh form (DP_F16_FAST / DP_F16_FAST32; bf16 always uses it)
+    int* range_flag;                             // sticky bit 0: a projected feature beyond the range where the edge kernels' f16 adds stay finite
 };
 
 // debug timeline of CTA 0: role 0 = compute warp 0, 1 = MMA thread, 2 = TMA thread; 16 slots per (role, row)
@@ -369,9 +370,11 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 float v[16];
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
                 __half* d = dst + (size_t)i0 * a.ldp;
+                float big = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
-                    if (i0 + j < n_valid) *d = __float2half_rn(v[j] + bias);
+                    if (i0 + j < n_valid) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
+                if (big > 32000.f) atomicOr(a.range_flag, 1);                        // pq is f16 (pre-halved): Pa' + Pb' must stay finite
             }
             release_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
@@ -686,9 +689,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
                 float v[16];
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + i0, v);
                 __half* d = a.pq + (size_t)(n0_pair + owner * a.stride + l0) * a.ldp + (size_t)b * 256 + ch;
+                float big = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
-                    if (l0 + j < nvo) *d = __float2half_rn(v[j] + bias);
+                    if (l0 + j < nvo) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
+                if (big > 32000.f) atomicOr(a.range_flag, 1);
             }
             release_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
@@ -731,6 +736,7 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
     a.dbg = h->dbg;
     a.fast_silu = (h->precision == DP_F16_FAST || h->precision == DP_F16_FAST32) ? 1 : 0;
+    a.range_flag = p.nan_flag + 2;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;
     // whole waves of SMs: the fewest waves that fit NT-node tiles, then the smallest stride that keeps that count

@@ -349,20 +349,30 @@ class ConditionalDDPM(torch.nn.Module, ScheduleMixin):
         noise = None if self.noise_seed is not None and 'sample_gaussian' not in self.__dict__ else \
             self._draw(timesteps + 2, (len(phar_mask), nd + self.phar_nf), device)
         norm = (float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]))
-        for attempt in range(2):
+        grown = False
+        while True:
             xh_pocket = xh0_pocket.detach().to(torch.float32).contiguous().clone()
             res = h.sample(xh_pocket, noise, seed=self.noise_seed or 0, sample_ids=self.sample_ids,
                            return_frames=return_frames, norm=norm)
             fl = h.flags()                                    # ONE host read for the whole run
-            if not fl.edge_overflow:
-                break
-            # the radius graph outgrew the planned edge capacity (the device truncated it, memory-safe): re-plan with
-            # the edge count it reported and run again on the same noise
-            h.reset_flags()
-            if attempt == 1:
-                raise _lib.DiffPharError(f"edge buffer overflow persists at capacity {cap}")
-            cap = int(fl.edge_overflow * 1.25) + 1024
-            h.grow_edge_capacity(cap)
+            if fl.edge_overflow:
+                # the radius graph outgrew the planned edge capacity (the device truncated it, memory-safe): re-plan
+                # with the edge count it reported and run again on the same noise
+                h.reset_flags()
+                if grown:
+                    raise _lib.DiffPharError(f"edge buffer overflow persists at capacity {cap}")
+                cap = int(fl.edge_overflow * 1.25) + 1024
+                h.grow_edge_capacity(cap)
+                grown = True
+                continue
+            if fl.f16_range and self.dynamics.precision not in ("fp32", "tf32"):
+                # features or squared distances left f16's range (no cutoff and far-apart points, or very large
+                # activations): the 16-bit result would differ from the reference — repeat with fp32 storage
+                print(f'Warning: f16 range exceeded (flag {fl.f16_range}); re-running with tf32 tensor-core tiles.')
+                h.reset_flags()
+                self.dynamics.set_precision("tf32")
+                continue
+            break
         out, frames_phar, frames_pocket = res if return_frames > 1 else (res, None, None)
         if fl.nan_resets:
             print('Warning: detected nan, resetting EGNN output to zero.')

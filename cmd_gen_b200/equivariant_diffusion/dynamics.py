@@ -162,6 +162,12 @@ class EGNNDynamics(nn.Module):
             fl = h.flags()
             if fl.edge_overflow:
                 raise _lib.DiffPharError("edge buffer overflow persists after re-planning")
+        if fl.f16_range and self.precision not in ("fp32", "tf32"):
+            print(f'Warning: f16 range exceeded (flag {fl.f16_range}); re-running with tf32 tensor-core tiles.')
+            h.reset_flags()
+            self.set_precision("tf32")
+            out_p, out_r = h.dynamics_forward(xh_phars, xh_residues, t.to(torch.float32), want_residues=True)
+            fl = h.flags()
         if fl.nan_resets:
             print('Warning: detected nan, resetting EGNN output to zero.')
             h.reset_flags()

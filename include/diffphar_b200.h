@@ -76,6 +76,11 @@ typedef struct dp_flags {
     float last_max_cog;           /* max |sum_sample x_phar| after the final step */
     int64_t last_n_edges;         /* E of the most recent graph build */
     int64_t last_n_edges_phar;    /* E_p: edges whose row is a phar node */
+    int32_t f16_range;            /* 16-bit modes only, sticky: bit 0 = a pre-projected feature left the range in which f16
+                                     sums stay finite (|P| > 32 000), bit 1 = a squared distance was clamped to 60 000 by the
+                                     packed-f16 first layer (edge_cutoff = None with far-apart points): the result differs
+                                     from the reference — re-run in DP_TF32 / DP_FP32 (the Python mirror does) */
+    int32_t reserved;
 } dp_flags;
 
 const char* dp_last_error(void);
