@@ -417,8 +417,6 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     p.seg_lanes = h->seg_mode == 2 || (h->seg_mode == 0 && (p.max_nodes >= 512 || ecap / UNIT_TC + 2 >= (int64_t)(1 << 20)));
     p.n_lanes = p.seg_lanes ? 4 * h->sm_count : 0;
     DP_CHECK(p.n_lanes <= MAX_LANES, DP_ERR_INVALID, "%d SMs: more segmented-sum lanes than agg_src can encode", h->sm_count);
-    DP_CHECK((ecap / UNIT_TC + 2) * (int64_t)(p.seg_lanes ? p.n_lanes : 1) < (int64_t)2147483000, DP_ERR_INVALID,
-             "edge capacity %lld too large for the 32-bit lane arithmetic of the segmented sum", (long long)ecap);
     DP_CHECK(p.seg_lanes || ecap / UNIT_TC + 2 < (int64_t)(1 << 20), DP_ERR_INVALID,
              "edge capacity %lld too large for the per-unit segmented-sum scheme (set DIFFPHAR_SEG=lanes)", (long long)ecap);
     DP_CHECK((int64_t)p.N + 2 * (ecap / UNIT_TC + 2 + MAX_LANES) < (int64_t)2147483000, DP_ERR_INVALID, "batch too large for int32 row indexing");

@@ -71,10 +71,12 @@ __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf
 //     share their Pa rows in L1: measured 17 % faster than lanes at this degree); a "lane" is then a single unit,
 //     l = u, and a row crossing 16-edge boundaries is stored as one partial row per unit.
 // Partial row 2 l + slot: slot 0 = the row that contains the lane's first edge, slot 1 = the row that starts inside
-// the lane and runs past its end.  U L < 2^31 is checked at plan time: 32-bit arithmetic throughout.
+// the lane and runs past its end.
 // ---------------------------------------------------------------------------
-__host__ __device__ __forceinline__ unsigned lane_first_unit(unsigned l, unsigned U, unsigned L) { return l * U / L; }
-__host__ __device__ __forceinline__ unsigned lane_of_unit(unsigned u, unsigned U, unsigned L) { return ((u + 1u) * L - 1u) / U; }
+// 64-bit products: U L reaches 2^32 for a config-3 batch of 512 samples (41 M edges, 592 lanes); the divisions run a
+// few times per CTA / per row, never per edge (edge_dst only asks for rows that cross a lane boundary)
+__host__ __device__ __forceinline__ unsigned lane_first_unit(unsigned l, unsigned U, unsigned L) { return (unsigned)((unsigned long long)l * U / L); }
+__host__ __device__ __forceinline__ unsigned lane_of_unit(unsigned u, unsigned U, unsigned L) { return (unsigned)((((unsigned long long)u + 1ull) * L - 1ull) / U); }
 // agg_src[row] (written by the graph builder's fill pass, read by every consumer of the aggregate):
 //   >= 0      : the whole sum is agg[row]
 //   AGG_EMPTY : the row has no edges

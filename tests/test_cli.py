@@ -58,6 +58,15 @@ def test_pocket_from_ligand_matches_reference_rule(tmp_path):
         pdbio.pocket_from_ligand(res, "A:777")
 
 
+def test_pocket_from_ligand_keeps_standard_amino_acids_written_as_hetatm(tmp_path):
+    """utils.py:109-117 filters on is_aa(resname, standard=True) only — the record type plays no role — and its ligand
+    skip (`residue.id[1] == resi`, int vs str) never fires: a peptide ligand made of a standard residue is kept."""
+    text = PDB_TEXT.replace("ENDMDL", "HETATM   12  CA  SER A 502      12.000  11.000  10.000  1.00 20.00           C\nENDMDL")
+    res = pdbio.read_pdb(write(tmp_path, text))
+    assert [r.resseq for r in pdbio.pocket_from_ligand(res, "A:501")] == [10, 11, 502]
+    assert [r.resseq for r in pdbio.pocket_from_ligand(res, "A:502")] == [10, 11, 502]      # the ligand itself is a standard residue
+
+
 def test_resi_list_and_pocket_tensors(tmp_path):
     res = pdbio.read_pdb(write(tmp_path))
     sel = pdbio.select_residues(res, ["A:11", "A:10"])
