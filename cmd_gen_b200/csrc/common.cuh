@@ -218,7 +218,7 @@ struct Plan {
     unsigned* row_bitmap = nullptr;  // [N][bitmap_words]: per-row hit bitmap over the sample's nodes, count pass -> fill pass
     int bitmap_words = 0;        // ceil(max nodes per sample / 32)
     int fused_graph = 0;         // one-launch scan builder (graph.cu radius_rows_fused_kernel): small samples, units scheme
-    unsigned long long* scan_status = nullptr;   // [ceil(N / 64)] look-back status words of that kernel
+    unsigned long long* scan_status = nullptr;   // [ceil(N / 32)] look-back status words of that kernel
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
@@ -345,6 +345,7 @@ struct EdgeArgs {
     float* x_next;                                   // coord == 1, tcgen05 path: the kernel finishes the phar rows itself (x + masked row sum)
     float norm_constant, coords_range, norm_factor; int mean;   // ... with these (coord2diff, egnn_new.py:91, 283-291)
     int coord; int attention; int use_tanh;
+    int coord_rows;                                  // coord == 1, tcgen05 path: every CTA owns a contiguous range of phar rows (tc_edge.cu)
     long long* trace;                                // debug timeline (dp_debug_trace), normally null
     int* range_flag;                                 // tcgen05 path: sticky f16-range bits (Plan::nan_flag + 2)
 };

@@ -123,15 +123,16 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
 // ---- one-launch builder for small samples (Calpha pockets) ----------------------------------------
 // count -> scan -> fill in ONE kernel: the three-launch version costs ~29 us at config-2 size (N = 10 k, 158 nodes per
 // sample), almost all of it launch latency and the single-CTA scan, and only ~10 us of it hide beside the first
-// projection.  Here a CTA owns 64 consecutive rows (8 warps x 8 rows):
-//   A  every warp sweeps its rows' samples once and keeps the 32-candidate ballots in registers (lane c = chunk c:
+// projection.  Here a CTA owns 32 consecutive rows, one per warp (a first version with 8 rows per warp serialised
+// eight latency-bound sweeps and was slower than three launches):
+//   A  every warp sweeps its row's sample once and keeps the 32-candidate ballots in a register (lane c = chunk c:
 //      a sample of < ~960 nodes has at most 32 chunks), degrees go to shared memory;
-//   B  warp 0 scans the 64 degrees and obtains the CTA's base offset by decoupled look-back over per-CTA status words
-//      (aggregate published at once, inclusive prefix as soon as the predecessors' are known; 32 predecessors per
-//      round trip) — CTAs are dispatched in index order and never wait for a later one;
+//   B  warp 0 scans the 32 degrees and publishes the CTA's total; the whole CTA then sums its predecessors' status
+//      words (1024 per round trip; inclusive prefixes short-cut larger grids) — CTAs are dispatched in index order and
+//      never wait for a later one;
 //   C  the fill replays the kept ballots: no second distance sweep, only d0 of the hits is recomputed.
 // Units scheme of the segmented sum only (edge_dst / agg_src need no global edge count there); identical output.
-constexpr int FUSED_ROWS = 64;
+constexpr int FUSED_ROWS = 32;                   // rows per CTA = warps per CTA: ONE row per warp (rows in flight hide the L2 round trips of a sweep)
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_VAL = (1ull << 40) - 1ull;
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
@@ -145,76 +146,88 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) radius_rows_fused_kernel(GraphArgs a)
+__global__ void __launch_bounds__(32 * FUSED_ROWS) radius_rows_fused_kernel(GraphArgs a)
 {
     __shared__ int degs[FUSED_ROWS];
     __shared__ int excl[FUSED_ROWS];
     __shared__ long long base_s;
+    __shared__ unsigned long long total_s, sum_s;
+    __shared__ int first_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int row0 = blockIdx.x * FUSED_ROWS;
+    const int row = blockIdx.x * FUSED_ROWS + wid;
     pdl_launch_dependents();
     pdl_wait();
-    // ---- A: one sweep per row, ballots kept
-    unsigned masks[8];
+    // ---- A: one sweep of the row's sample, ballots kept (lane c holds chunk c)
+    unsigned mask = 0u;
+    int found = 0, b = 0;
+    float xi = 0.f, yi = 0.f, zi = 0.f;
+    int lo[2] = {0, 0}, hi[2] = {0, 0};
+    if (row < a.N) {
+        b = a.sample_of[row];
+        xi = a.x[3 * row]; yi = a.x[3 * row + 1]; zi = a.x[3 * row + 2];
+        lo[0] = a.phar_off[b]; lo[1] = a.Np + a.res_off[b];
+        hi[0] = a.phar_off[b + 1]; hi[1] = a.Np + a.res_off[b + 1];
+        int chunk = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = row0 + wid * 8 + i;
-        masks[i] = 0u;
-        int found = 0;
-        if (row < a.N) {
-            const int b = a.sample_of[row];
-            const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
-            const int lo[2] = {a.phar_off[b], a.Np + a.res_off[b]};
-            const int hi[2] = {a.phar_off[b + 1], a.Np + a.res_off[b + 1]};
-            int chunk = 0;
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
-                    const int j = j0 + lane;
-                    bool hit = false;
-                    if (j < hi[part]) {
-                        const float d2 = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
-                        hit = (a.cutoff < 0.f) || (__fsqrt_rn(d2) <= a.cutoff);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, hit);
-                    if (lane == chunk) masks[i] = m;
-                    found += __popc(m);
+        for (int part = 0; part < 2; ++part) {
+            for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
+                const int j = j0 + lane;
+                bool hit = false;
+                if (j < hi[part]) {
+                    const float d2 = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                    hit = (a.cutoff < 0.f) || (__fsqrt_rn(d2) <= a.cutoff);
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == chunk) mask = m;
+                found += __popc(m);
             }
         }
-        if (lane == 0) degs[wid * 8 + i] = found;
     }
+    if (lane == 0) degs[wid] = found;
     __syncthreads();
-    // ---- B: CTA scan + decoupled look-back
+    // ---- B: CTA scan, then the CTA's base offset = sum of the predecessors' totals.  The whole CTA looks back, 1024
+    // predecessors per round trip (thread t reads CTA c - 1 - t): at config-2 size (316 CTAs) one round trip after the
+    // slowest predecessor published; a 32-wide look-back would propagate the prefix 32 CTAs per round trip — all CTAs
+    // run at the same time here, so there are no long-finished predecessors to short-cut to.  Larger grids stop at the
+    // nearest predecessor whose INCLUSIVE prefix is known.
     if (wid == 0) {
-        const int v0 = degs[2 * lane], v1 = degs[2 * lane + 1];
-        int incl = v0 + v1;
+        const int v = degs[lane];
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        excl[2 * lane] = incl - v0 - v1;
-        excl[2 * lane + 1] = incl - v1;
-        const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
-        unsigned long long prefix = 0ull;
-        if (blockIdx.x > 0) {
-            if (lane == 0) st_release_u64(a.status + blockIdx.x, ST_AGG | total);
-            for (int j = (int)blockIdx.x - 1;; j -= 32) {
-                const int idx = j - lane;
-                unsigned long long v = ST_INCL;                                  // before CTA 0: inclusive prefix 0
-                if (idx >= 0) { do { v = ld_acquire_u64(a.status + idx); } while (v == 0ull); }
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-                const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;          // nearest predecessor whose inclusive prefix is known
-                unsigned long long c = lane <= first ? (v & ST_VAL) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                prefix += c;
-                if (incl_mask) break;
-            }
+        excl[lane] = incl - v;
+        if (lane == 31) {
+            total_s = (unsigned long long)incl;
+            if (blockIdx.x > 0) st_release_u64(a.status + blockIdx.x, ST_AGG | (unsigned long long)incl);
+            sum_s = 0ull; first_s = 0x7fffffff;
         }
-        if (lane == 0) {
-            st_release_u64(a.status + blockIdx.x, ST_INCL | (prefix + total));
+    }
+    __syncthreads();
+    {
+        const int t = threadIdx.x;
+        unsigned long long prefix = 0ull;
+        for (int jb = (int)blockIdx.x - 1; blockIdx.x > 0; jb -= 32 * FUSED_ROWS) {
+            const int idx = jb - t;
+            unsigned long long sv = ST_INCL;                                     // before CTA 0: inclusive prefix 0
+            if (idx >= 0) { do { sv = ld_acquire_u64(a.status + idx); } while (sv == 0ull); }
+            const bool is_incl = (sv >> 62) == 2ull;
+            const unsigned im = __ballot_sync(0xffffffffu, is_incl);
+            if (im && lane == 0) atomicMin(&first_s, t + __ffs(im) - 1);         // nearest predecessor with a known inclusive prefix
+            __syncthreads();
+            const int first = first_s;                                            // 0x7fffffff: none in this window
+            unsigned long long c = t <= first ? (sv & ST_VAL) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0 && c) atomicAdd(&sum_s, c);
+            __syncthreads();
+            prefix = sum_s;
+            if (first != 0x7fffffff) break;
+        }
+        if (t == 0) {
+            st_release_u64(a.status + blockIdx.x, ST_INCL | (prefix + total_s));
             base_s = (long long)prefix;
             if (blockIdx.x == gridDim.x - 1) {                                   // the edge count: published clamped, see scan_rowptr_kernel
-                const long long E = (long long)(prefix + total);
+                const long long E = (long long)(prefix + total_s);
                 const int Ec = (int)(E < a.ecap ? E : a.ecap);
                 const_cast<int*>(a.rowptr)[a.N] = Ec;
                 a.counts[0] = Ec;
@@ -225,41 +238,32 @@ __global__ void __launch_bounds__(256) radius_rows_fused_kernel(GraphArgs a)
     }
     __syncthreads();
     // ---- C: fill from the kept ballots
-    const long long cta_base = base_s;
+    if (row >= a.N) return;
+    const long long base = base_s + excl[wid];
+    const long long row_end = base + found;
+    const RowSeg seg = row_seg(a.N, base, row_end, 0, 0);
+    if (lane == 0) {
+        a.agg_src[row] = row_agg_src(seg, row, base, row_end);
+        const int bc = (int)(base < a.ecap ? base : a.ecap);
+        const_cast<int*>(a.rowptr)[row] = bc;
+        if (row == a.Np) a.counts[1] = bc;                                       // E_p: rows [0, Np) are the phar nodes
+    }
+    int chunk = 0, done = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = row0 + wid * 8 + i;
-        if (row >= a.N) continue;
-        const long long base = cta_base + excl[wid * 8 + i];
-        const long long row_end = base + degs[wid * 8 + i];
-        const RowSeg seg = row_seg(a.N, base, row_end, 0, 0);
-        if (lane == 0) {
-            a.agg_src[row] = row_agg_src(seg, row, base, row_end);
-            const int bc = (int)(base < a.ecap ? base : a.ecap);
-            const_cast<int*>(a.rowptr)[row] = bc;
-            if (row == a.Np) a.counts[1] = bc;                                   // E_p: rows [0, Np) are the phar nodes
-        }
-        const int b = a.sample_of[row];
-        const float xi = a.x[3 * row], yi = a.x[3 * row + 1], zi = a.x[3 * row + 2];
-        const int lo[2] = {a.phar_off[b], a.Np + a.res_off[b]};
-        const int hi[2] = {a.phar_off[b + 1], a.Np + a.res_off[b + 1]};
-        int chunk = 0, found = 0;
-#pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
-                const unsigned m = __shfl_sync(0xffffffffu, masks[i], chunk);
-                if ((m >> lane) & 1u) {
-                    const int j = j0 + lane;
-                    const long long pos = base + found + __popc(m & ((1u << lane) - 1u));
-                    if (pos < a.ecap) {
-                        a.col[pos] = j;
-                        a.erow[pos] = row;
-                        a.d0[pos] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
-                        a.edst[pos] = edge_dst(seg, row, base, row_end, pos);
-                    }
+    for (int part = 0; part < 2; ++part) {
+        for (int j0 = lo[part]; j0 < hi[part]; j0 += 32, ++chunk) {
+            const unsigned m = __shfl_sync(0xffffffffu, mask, chunk);
+            if ((m >> lane) & 1u) {
+                const int j = j0 + lane;
+                const long long pos = base + done + __popc(m & ((1u << lane) - 1u));
+                if (pos < a.ecap) {
+                    a.col[pos] = j;
+                    a.erow[pos] = row;
+                    a.d0[pos] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+                    a.edst[pos] = edge_dst(seg, row, base, row_end, pos);
                 }
-                found += __popc(m);
             }
+            done += __popc(m);
         }
     }
 }
@@ -557,7 +561,7 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
         // one launch (+ the status clear): see radius_rows_fused_kernel
         const int n_cta = (p.N + FUSED_ROWS - 1) / FUSED_ROWS;
         DP_CUDA(cudaMemsetAsync(p.scan_status, 0, (size_t)n_cta * sizeof(unsigned long long), st));
-        DP_CUDA(launch_kernel(h->pdl, radius_rows_fused_kernel, dim3(n_cta), dim3(256), 0, st, a));
+        DP_CUDA(launch_kernel(h->pdl, radius_rows_fused_kernel, dim3(n_cta), dim3(32 * FUSED_ROWS), 0, st, a));
         h->launches -= 2;
     } else {
         DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));

@@ -59,7 +59,8 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
-constexpr int REGS_MMA = 40;                      // 32 spilled ~20 registers around the weight fill (tcgen05.cp descriptors); 40 is what the pool has left
+constexpr int REGS_MMA = 32;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless,
+                                                  // and the 8 spare registers keep the producers' setmaxnreg.inc from waiting on every dec
 #ifndef EDGE_REGS_PACKED_PRODUCER
 #define EDGE_REGS_PACKED_PRODUCER 104
 #define EDGE_REGS_PACKED_EPILOGUE 64
@@ -135,17 +136,18 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     int s_row = 0, s_col = 0; float s_d0 = 0.f;
-    if (!a.coord && !a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+    const bool crow = a.coord && a.coord_rows;           // coordinate mode with row-owned tiles (default); else the message-mode split
+    if (!crow && !a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
     // Coordinate mode: the CTA OWNS a contiguous range of phar rows [c_r0, c_r1) — hence a contiguous CSR edge range
     // [c_e0, c_e1) — so that after its tiles it can finish those rows itself (coord_diff * scalar, row sum, x update:
     // egnn_new.py:91-103) without any cross-CTA dependency: no second launch, no global round trip through another kernel.
-    const int c_r0 = a.coord ? (int)((long long)blockIdx.x * a.n_moving / (int)gridDim.x) : 0;
-    const int c_r1 = a.coord ? (int)((long long)(blockIdx.x + 1) * a.n_moving / (int)gridDim.x) : 0;
-    const int c_e0 = a.coord ? a.rowptr[c_r0] : 0, c_e1 = a.coord ? a.rowptr[c_r1] : 0;
-    const int E = a.coord ? c_e1 : *a.n_edges;               // exclusive end of the edges this CTA may touch
+    const int c_r0 = crow ? (int)((long long)blockIdx.x * a.n_moving / (int)gridDim.x) : 0;
+    const int c_r1 = crow ? (int)((long long)(blockIdx.x + 1) * a.n_moving / (int)gridDim.x) : 0;
+    const int c_e0 = crow ? a.rowptr[c_r0] : 0, c_e1 = crow ? a.rowptr[c_r1] : 0;
+    const int E = crow ? c_e1 : *a.n_edges;                  // exclusive end of the edges this CTA may touch
 
     // ---- prologue
     if (tid == 0) {
@@ -198,15 +200,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     // for every CTA that has a long lane and one (empty, skipped by has_unit) tile too many for the others — which
     // finish no later than the CTAs that need it.  Idle CTAs fall through with 0.
     int my_tiles;
-    if (a.coord) my_tiles = (c_e1 - c_e0 + TILE - 1) / TILE;
+    if (crow) my_tiles = (c_e1 - c_e0 + TILE - 1) / TILE;
     else if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
     else my_tiles = max(0, ((E + TILE - 1) / TILE - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
     // group g's 16 edges of tile `it` start at edge_base(g) + it * edge_step, and exist while it < unit_count(g)
     //   coordinate mode: tiles are 64 consecutive edges from the CTA's first edge (any alignment: nothing is keyed on units)
-    const bool lanes = a.contig && !a.coord;
-    const int edge_step = a.coord ? TILE : (lanes ? UNIT_TC : TILE * (int)gridDim.x);
+    const bool lanes = a.contig && !crow;
+    const int edge_step = crow ? TILE : (lanes ? UNIT_TC : TILE * (int)gridDim.x);
     auto unit_base = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
-    auto edge_base = [&](int g) { return a.coord ? c_e0 + UNIT_TC * g : UNIT_TC * unit_base(g); };
+    auto edge_base = [&](int g) { return crow ? c_e0 + UNIT_TC * g : UNIT_TC * unit_base(g); };
     auto unit_count = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
 
     if (wid >= MMA_WARP) {
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
         };
         int n_row, n_col; float n_d0;
-        if (a.contig || a.coord) {
+        if (a.contig || crow) {
             load_rc(0, m_row, m_col, m_d0);
         } else {
             const bool ok = my_tiles > 0 && lane < 8 && ebase + e_off < E;                 // the speculative loads were real edges
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
         const int l74 = (lane & 7) << 4;
 
+        bool range_bad = false;
         for (int it = 0; it < my_tiles; ++it) {
             const int xs = it % N_XS;
             int f_row, f_col; float f_d0;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 m_rd = *reinterpret_cast<const uint32_t*>(&t);
                 // beyond f16's range the clamp makes this edge differ from the reference (only reachable without a cutoff):
                 // flagged, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
-                if (fmaxf(m_r2, m_d0) > 60000.f) atomicOr(a.range_flag, 2);
+                range_bad |= fmaxf(m_r2, m_d0) > 60000.f;                                    // reported once, after the tile loop
             }
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
@@ -422,6 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             m_r2 = n_moving ? dist2(xr0, xr1, xr2, xc0, xc1, xc2) : n_d0;
             n_row = f_row; n_col = f_col; n_d0 = f_d0;
         }
+        if (range_bad) atomicOr(a.range_flag, 2);
     } else {
         // ================================ epilogue ================================
         if (regs_epilogue(MODE) > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));
@@ -534,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 7);
         }
-        if (a.coord && !(a.dbg & 8)) {                                                   // dbg bit 3: A/B against the stand-alone finish launch
+        if (crow && !(a.dbg & 8)) {                                                      // dbg bit 3: A/B against the stand-alone finish launch
             // ---- finish the CTA's own phar rows (replaces coord_finish_kernel): eight lanes per row, lane l takes the row's
             // edges l, l + 8, ... in CSR order, a fixed-order shuffle tree combines them — deterministic, no atomics, the
             // same arithmetic in the same order as the stand-alone kernel (small.cu) the FFMA path still launches.

@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             publish(2);
         }
         // ---- epilogue 3: projection blocks -> P (f16: halves the edge kernels' gather bytes and staging registers)
+        float big = 0.f;                                                             // largest |P'| this thread stored (f16 range guard)
         for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
             if (b == skip_b) continue;
             const int acc = cnt & 1;
@@ -370,15 +371,14 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 float v[16];
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + half * NT + i0, v);
                 __half* d = dst + (size_t)i0 * a.ldp;
-                float big = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
                     if (i0 + j < n_valid) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
-                if (big > 32000.f) atomicOr(a.range_flag, 1);                        // pq is f16 (pre-halved): Pa' + Pb' must stay finite
             }
             release_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
         }
+        if (big > 32000.f) atomicOr(a.range_flag, 1);                                // pq is f16 (pre-halved): Pa' + Pb' must stay finite
     }
     tc_fence_before();
     __syncthreads();
@@ -674,6 +674,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
             publish(2, -1, nullptr);
         }
         // ---- epilogue 3: projection blocks -> P (f16)
+        float big = 0.f;
         for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
             if (b == skip_b) continue;
             const int acc = cnt & 1;
@@ -689,15 +690,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
                 float v[16];
                 tmem_ld16(tmem_base + acc * ACC_COLS + t_lane + i0, v);
                 __half* d = a.pq + (size_t)(n0_pair + owner * a.stride + l0) * a.ldp + (size_t)b * 256 + ch;
-                float big = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j, d += a.ldp)
                     if (l0 + j < nvo) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
-                if (big > 32000.f) atomicOr(a.range_flag, 1);
             }
             release_acc(acc);
             if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
         }
+        if (big > 32000.f) atomicOr(a.range_flag, 1);
     }
     tc_fence_before();
     __syncthreads();
