@@ -11,15 +11,17 @@ CPU half (not gpu): the oracle restatement against the same fixtures.  GPU half:
 precisions against the reference's fp64 outputs — not against the library's own fp32 mode.
 
 Stated tolerances (per denoiser call; `hs` = max |reference feature output|, `xs` = max |input coordinate|,
-`vs` = max |reference velocity|):
-  fp32    : features 2e-5 hs, velocity 1e-5 xs           (the reference's own fp32-vs-fp64 error: 5e-8 / 2e-6)
-  tf32    : features 1e-4 hs, velocity 1e-5 xs + 0.02 vs  (tcgen05 kind::tf32 tiles, fp32 storage: 10-bit mantissa operands)
-  f16     : features 1e-4 hs, velocity 1e-5 xs + 0.02 vs  (f16 operands: the same 10-bit mantissa, 16-bit storage of pq)
-  f16fast : features 2e-4 hs, velocity 1e-5 xs + 0.03 vs
-  bf16    : features 1e-3 hs, velocity 1e-5 xs + 0.05 vs
-  (config 3 / 5: feature bounds x4 — ~40 messages per node and up to 9 blocks accumulate operand rounding)
-End to end after 500 steps (config 1, `scale` = max |final coordinate| = 1 097): fp32 max(10 x the reference's own
-fp32-vs-fp64 error, 1e-4 scale); tf32 / f16 3e-4, f16fast 4e-4, bf16 1e-3 of scale; types identical (fp32) / >= 90 %.
+`vs` = max |reference velocity|; measured on a B200 in profiles/r05a_parity_errors.txt):
+  fp32    : features 2e-6 hs, velocity 1e-6 xs           (measured 1.0e-7 / 1.8e-6 = the reference's own fp32-vs-fp64 error)
+  tf32    : features 5e-5 hs, velocity 1e-6 xs + 0.02 vs  (tcgen05 kind::tf32 tiles, fp32 storage; measured 0.6 - 1.1e-5)
+  f16     : features 5e-5 hs, velocity 1e-6 xs + 0.02 vs  (f16 operands, the same 10-bit mantissa; measured 0.5 - 1.0e-5)
+  f16fast : features 5e-5 hs, velocity 1e-6 xs + 0.03 vs  (measured 0.6 - 1.2e-5)
+  bf16    : features 5e-4 hs, velocity 1e-6 xs + 0.05 vs  (measured 0.5 - 1.0e-4)
+  the same bounds at every configuration (config 3 / 5: ~40 messages per node, up to 9 blocks — no larger error measured).
+  The velocity cancels at coordinate magnitude: 1e-6 xs is ~ 8 ulp of the coordinates.
+End to end after 500 steps (config 1, `scale` = max |final coordinate| = 1 097; the reference's own fp32-vs-fp64
+difference is 2.7e-3 = 2.4e-6 scale): fp32 max(3 x that, 1e-5 scale); tf32 / f16 3e-5, f16fast 5e-5, bf16 2e-4 of scale
+(measured 1.6 - 2.7e-3 in every mode); types identical in every mode (measured), required: fp32 all, others >= 98 %.
 BASELINE config 5's "bf16 MLP tiles vs TF32 accuracy check": test_config5_bf16_tiles_vs_tf32_accuracy.
 """
 import os
@@ -34,8 +36,8 @@ from oracle import large_cases as lc
 from tests.helpers import GOLDEN, load, T
 
 DEV = "cuda:0"
-TC_TOL = {"tf32": (1e-4, 0.02), "f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
-DEEP = {"config2": 1.0, "config3": 4.0, "config5": 4.0}
+TC_TOL = {"tf32": (5e-5, 0.02), "f16": (5e-5, 0.02), "f16fast": (5e-5, 0.03), "bf16": (5e-4, 0.05)}
+DEEP = {"config2": 1.0, "config3": 1.0, "config5": 1.0}
 PRECISIONS = ["fp32", "tf32", "f16", "f16fast", "bf16"]
 
 
@@ -157,9 +159,9 @@ def test_dynamics_at_config_size_vs_reference(name, prec):
         eh = float(np.abs(out_p[:, 3:] - rp[:, 3:]).max())
         ex = float(np.abs(out_p[:, :3] - rp[:, :3]).max())
         if prec == "fp32":
-            tol_h, tol_x = 2e-5 * hs, 1e-5 * xs
+            tol_h, tol_x = 2e-6 * hs, 1e-6 * xs
         else:
-            tol_h, tol_x = DEEP[name] * TC_TOL[prec][0] * hs, 1e-5 * xs + TC_TOL[prec][1] * vs
+            tol_h, tol_x = DEEP[name] * TC_TOL[prec][0] * hs, 1e-6 * xs + TC_TOL[prec][1] * vs
         worst[float(tv)] = (eh / hs, ex, float(g[f"ref_err_h_{i}"]), float(g[f"ref_err_x_{i}"]))
         assert eh <= tol_h, (name, prec, tv, eh, tol_h)
         assert ex <= tol_x, (name, prec, tv, ex, tol_x)
@@ -167,7 +169,7 @@ def test_dynamics_at_config_size_vs_reference(name, prec):
             out_r = out_r.cpu().numpy()
             rs = max(1.0, float(g["eps_res_absmax_0"]))
             er = float(np.abs(out_r[:, 3:] - g["eps_res_f64as32_0"]).max())
-            assert er <= (2e-5 if prec == "fp32" else DEEP[name] * TC_TOL[prec][0]) * rs, (name, prec, er)
+            assert er <= (2e-6 if prec == "fp32" else DEEP[name] * TC_TOL[prec][0]) * rs, (name, prec, er)
             assert np.all(out_r[:, :3] == 0.0)
             worst["res"] = er / rs
     print(f"\n[parity] {name} {prec}: N={x.shape[0]} E={int(g['n_edges'])} worst (feature rel, velocity abs, ref fp32 err h, x) per t: {worst}")
@@ -184,11 +186,11 @@ def test_config1_all_500_steps_vs_reference(prec):
     d = lc.sampler_inputs("config1")
     assert np.allclose(lc.checksum(d["noise"]), g["noise_checksum"], rtol=0, atol=1e-6)
     cfg = d["cfg"]
-    bound_rel = {"fp32": None, "tf32": 3e-4, "f16": 3e-4, "f16fast": 4e-4, "bf16": 1e-3}[prec]
+    bound_rel = {"fp32": None, "tf32": 3e-5, "f16": 3e-5, "f16fast": 5e-5, "bf16": 2e-4}[prec]
     ref = g["xh_phar_f64"]
     scale = float(np.abs(ref[:, :3]).max())
     ref_err = float(np.abs(g["xh_phar_f32"][:, :3] - ref[:, :3]).max())
-    bound = max(10 * ref_err, 1e-4 * scale) if prec == "fp32" else bound_rel * scale
+    bound = max(3 * ref_err, 1e-5 * scale) if prec == "fp32" else bound_rel * scale
 
     def run(return_frames):
         ddpm = build_ddpm(cfg, d["wseed"], 500, prec)
@@ -204,7 +206,7 @@ def test_config1_all_500_steps_vs_reference(prec):
     print(f"\n[parity] config1 {prec}: 500 steps, scale {scale:.1f}, max |dx| {err:.3e} (bound {bound:.3e}, reference fp32 "
           f"vs fp64 {ref_err:.3e}), types identical {same:.2f}, pocket err {perr:.3e}")
     assert err <= bound and perr <= bound
-    assert same == 1.0 if prec == "fp32" else same >= 0.9
+    assert same == 1.0 if prec == "fp32" else same >= 0.98
     dxyz = got[:, :3] - ref[:, :3]
     for b in range(len(d["counts"])):                                   # north_star: per-sample RMSD
         assert np.sqrt((dxyz[g["mask_phar"] == b] ** 2).sum(1).mean()) <= bound
@@ -214,14 +216,20 @@ def test_config1_all_500_steps_vs_reference(prec):
     (fr_phar, fr_pocket, _, _), _ = run(10)
     assert fr_phar.shape[0] == 10
     assert np.abs(fr_phar[0].cpu().numpy()[:, :3] - ref[:, :3]).max() <= bound
+    worst_traj, worst_feat = 0.0, 0.0
     for idx in range(1, 10):
         rz = g["trace_z_f64"][9 - idx]                                  # frame idx holds s = 50 idx, i.e. call 500 - 50 idx
         zs = float(np.abs(rz[:, :3]).max())
         gz = fr_phar[idx].cpu().numpy()
         r_err = float(np.abs(g["trace_z_f32"][9 - idx] - rz).max())
-        b_x = max(10 * r_err, 1e-4 * zs) if prec == "fp32" else bound_rel * zs
-        assert np.abs(gz[:, :3] - rz[:, :3]).max() <= b_x, (idx, prec)
-        assert np.abs(gz[:, 3:] - 4.0 * rz[:, 3:]).max() <= (1e-4 if prec == "fp32" else 10 * bound_rel) * max(1.0, np.abs(4 * rz[:, 3:]).max())
+        b_x = max(3 * r_err, 1e-5 * zs) if prec == "fp32" else max(3 * r_err, 2 * bound_rel * zs)
+        e_x = float(np.abs(gz[:, :3] - rz[:, :3]).max())
+        e_h = float(np.abs(gz[:, 3:] - 4.0 * rz[:, 3:]).max()) / max(1.0, float(np.abs(4 * rz[:, 3:]).max()))
+        worst_traj = max(worst_traj, e_x / zs)
+        worst_feat = max(worst_feat, e_h)
+        assert e_x <= b_x, (idx, prec, e_x, b_x)
+        assert e_h <= {"fp32": 1e-4, "tf32": 3e-3, "f16": 3e-3, "f16fast": 4e-3, "bf16": 1e-2}[prec], (idx, prec, e_h)
+    print(f"[parity] config1 {prec}: trajectory every 50 steps: worst |dz_x| / scale {worst_traj:.3e}, worst feature error {worst_feat:.3e}")
 
 
 @pytest.mark.gpu
@@ -243,4 +251,4 @@ def test_config5_bf16_tiles_vs_tf32_accuracy():
         err[prec] = max(e_p, e_r)
     print(f"\n[parity] config5 accuracy vs reference fp64 (max feature error / max |ref|): {err}")
     assert err["tf32"] < err["bf16"] and err["f16"] < err["bf16"]
-    assert err["tf32"] <= 4e-4 and err["bf16"] <= 4e-3
+    assert err["tf32"] <= 5e-5 and err["bf16"] <= 5e-4
