@@ -146,6 +146,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_TMA_FILL")) h->tma_fill = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_COORD_ROWS")) h->coord_rows = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "scan3") ? 3 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
@@ -445,7 +446,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.deg, p.N); cv.take(&p.rowptr, p.N + 1); cv.take(&p.agg_src, p.N);
     cv.take(&p.col, ecap); cv.take(&p.erow, ecap); cv.take(&p.edst, ecap); cv.take(&p.d0, ecap); cv.take(&p.escal, ecap);
     cv.take(&p.counts, 4);
-    cv.take(&p.scan_status, (size_t)p.N / 32 + 2);
+    cv.take(&p.scan_status, (size_t)p.N / 8 + 2);
     if (p.use_cells) {
         cv.take(&p.cell_start, (size_t)B * (CELLS_MAX + 1)); cv.take(&p.cell_nodes, p.N); cv.take(&p.cell_grid, (size_t)B * 8);
         p.bitmap_words = (p.max_nodes + 31) / 32;
@@ -648,7 +649,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr; q.range_flag = p.nan_flag + 2;
-            q.coord_rows = (h->dbg & 16) ? 0 : 1;      // dbg bit 4: round-1 tile split of the coordinate edges (same-box A/B)
+            q.coord_rows = h->coord_rows;              // DIFFPHAR_COORD_ROWS=1: row-owned tiles + in-kernel finish (measured slower, see tc_edge.cu)
             q.x_next = x_next; q.norm_constant = c.norm_constant; q.coords_range = c.coords_range;
             q.norm_factor = c.normalization_factor; q.mean = c.aggregation_mean;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;

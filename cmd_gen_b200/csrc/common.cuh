@@ -218,7 +218,7 @@ struct Plan {
     unsigned* row_bitmap = nullptr;  // [N][bitmap_words]: per-row hit bitmap over the sample's nodes, count pass -> fill pass
     int bitmap_words = 0;        // ceil(max nodes per sample / 32)
     int fused_graph = 0;         // one-launch scan builder (graph.cu radius_rows_fused_kernel): small samples, units scheme
-    unsigned long long* scan_status = nullptr;   // [ceil(N / 32)] look-back status words of that kernel
+    unsigned long long* scan_status = nullptr;   // [ceil(N / 8)] look-back status words of that kernel
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term
@@ -262,6 +262,8 @@ struct dp_handle {
     int sm_count = 148;
     int precision = 0;
     int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
+    int coord_rows = 0;                // DIFFPHAR_COORD_ROWS=1: coordinate-mode edge kernel with row-owned tiles that finishes its rows itself
+                                       // (one launch less per block, but measured 6 % slower per step: profiles/r05c_ab_summary.txt)
     int seg_mode = 0;                  // DIFFPHAR_SEG: 0 automatic, 1 units, 2 lanes (Plan::seg_lanes)
     int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
     int tma_fill = 1;                  // DIFFPHAR_TMA_FILL=0: resident weights through LDG + tcgen05.st (A/B; EdgeArgs::tma_fill)

@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
 //      never wait for a later one;
 //   C  the fill replays the kept ballots: no second distance sweep, only d0 of the hits is recomputed.
 // Units scheme of the segmented sum only (edge_dst / agg_src need no global edge count there); identical output.
-constexpr int FUSED_ROWS = 32;                   // rows per CTA = warps per CTA: ONE row per warp (rows in flight hide the L2 round trips of a sweep)
+constexpr int FUSED_ROWS = 8;                    // rows per CTA = warps per CTA: ONE row per warp (rows in flight hide the L2 round trips of a sweep).
+                                                 // 256-thread CTAs: five fit beside a resident node-kernel CTA (the builder runs forked beside the first
+                                                 // projection) — 1024-thread CTAs got one slot per SM there and ran in three waves
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_VAL = (1ull << 40) - 1ull;
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
@@ -185,17 +187,17 @@ __global__ void __launch_bounds__(32 * FUSED_ROWS) radius_rows_fused_kernel(Grap
     }
     if (lane == 0) degs[wid] = found;
     __syncthreads();
-    // ---- B: CTA scan, then the CTA's base offset = sum of the predecessors' totals.  The whole CTA looks back, 1024
-    // predecessors per round trip (thread t reads CTA c - 1 - t): at config-2 size (316 CTAs) one round trip after the
+    // ---- B: CTA scan, then the CTA's base offset = sum of the predecessors' totals.  The whole CTA looks back, 256
+    // predecessors per round trip at first (thread t reads CTA c - 1 - t): at config-2 size (1264 CTAs) a handful of round trips after the
     // slowest predecessor published; a 32-wide look-back would propagate the prefix 32 CTAs per round trip — all CTAs
     // run at the same time here, so there are no long-finished predecessors to short-cut to.  Larger grids stop at the
     // nearest predecessor whose INCLUSIVE prefix is known.
     if (wid == 0) {
-        const int v = degs[lane];
+        const int v = lane < FUSED_ROWS ? degs[lane] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        excl[lane] = incl - v;
+        if (lane < FUSED_ROWS) excl[lane] = incl - v;
         if (lane == 31) {
             total_s = (unsigned long long)incl;
             if (blockIdx.x > 0) st_release_u64(a.status + blockIdx.x, ST_AGG | (unsigned long long)incl);

@@ -141,9 +141,14 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
-    // Coordinate mode: the CTA OWNS a contiguous range of phar rows [c_r0, c_r1) — hence a contiguous CSR edge range
-    // [c_e0, c_e1) — so that after its tiles it can finish those rows itself (coord_diff * scalar, row sum, x update:
-    // egnn_new.py:91-103) without any cross-CTA dependency: no second launch, no global round trip through another kernel.
+    // Coordinate mode with row-owned tiles (EdgeArgs::coord_rows, DIFFPHAR_COORD_ROWS=1; OFF by default): the CTA OWNS a
+    // contiguous range of phar rows [c_r0, c_r1) — hence a contiguous CSR edge range [c_e0, c_e1) — so that after its
+    // tiles it can finish those rows itself (coord_diff * scalar, row sum, x update: egnn_new.py:91-103) without any
+    // cross-CTA dependency: no second launch.  Parity-green, but measured SLOWER on one box (profiles/r05c_ab_summary.txt:
+    // 356 vs 336 us per config-2 step): the split costs two more dependent L2 round trips before the first gather (rowptr,
+    // then metadata that can no longer be requested speculatively at kernel entry) and wakes all 148 CTAs for the 128 KB
+    // weight fill instead of 94; fusing the finish recovers only 7 of those 27 us.  The default keeps the message-mode
+    // tile split and the stand-alone coord_finish_kernel.
     const int c_r0 = crow ? (int)((long long)blockIdx.x * a.n_moving / (int)gridDim.x) : 0;
     const int c_r1 = crow ? (int)((long long)(blockIdx.x + 1) * a.n_moving / (int)gridDim.x) : 0;
     const int c_e0 = crow ? a.rowptr[c_r0] : 0, c_e1 = crow ? a.rowptr[c_r1] : 0;

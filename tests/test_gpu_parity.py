@@ -27,12 +27,15 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None):
-    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH);
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, coord_rows=None):
+    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "scan" takes
+    the one-launch kernel where it applies, "scan3" the three-launch version); coord_rows="1": the coordinate-mode edge kernel
+    with row-owned tiles that finishes its rows itself;
     seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
     node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel."""
     import os
-    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill}
+    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill,
+              "DIFFPHAR_COORD_ROWS": coord_rows}
     old = {k: os.environ.pop(k, None) for k in forced}
     for k, v in forced.items():
         if v:
@@ -56,7 +59,7 @@ def csr_to_coo(rowptr, col):
 
 
 # ----------------------------------------------------------------------------- K1
-@pytest.mark.parametrize("graph", ["scan", "cells"])
+@pytest.mark.parametrize("graph", ["scan", "scan3", "cells"])
 @pytest.mark.parametrize("name", CASES)
 def test_edges_bit_exact_vs_reference(name, graph):
     g = load(f"dynamics_{name}.npz")
@@ -70,8 +73,8 @@ def test_edges_bit_exact_vs_reference(name, graph):
     assert np.array_equal((rowptr[1:] - rowptr[:-1]).cpu().numpy(), ref_deg)
 
 
-@pytest.mark.parametrize("graph", ["scan", "cells"])
-@pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.05, 700, 12, 6), (0.05, 2000, 12, 3)])
+@pytest.mark.parametrize("graph", ["scan", "scan3", "cells"])
+@pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.0074, 300, 10, 90), (0.05, 700, 12, 6), (0.05, 2000, 12, 3)])
 def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B, graph):
     cfg = DynamicsConfig(residue_nf=20)
     h = make_handle(DynamicsConfig(n_layers=1), 0, graph=graph)
@@ -285,7 +288,8 @@ def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg)
         assert torch.equal(a2.cpu(), a) and torch.equal(r2.cpu(), r)
 
 
-@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}])
+@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}, {"coord_rows": "1"},
+                                    {"coord_rows": "1", "seg": "lanes"}])
 def test_alternative_kernel_paths_match_the_default(switch):
     """The switchable kernel variants kept for A/B runs (CTA-pair node kernel with tcgen05 cta_group::2 and DSMEM bulk
     exchange; LDG + tcgen05.st weight fill of the edge kernel) against the default path on a ragged batch: same
@@ -311,7 +315,7 @@ def test_alternative_kernel_paths_match_the_default(switch):
     assert (ap[:, 3:] - rp[:, 3:]).abs().max() <= tol_h * max(1.0, float(rp[:, 3:].abs().max()))
     assert (ar[:, 3:] - rr[:, 3:]).abs().max() <= tol_h * max(1.0, float(rr[:, 3:].abs().max()))
     assert (ap[:, :3] - rp[:, :3]).abs().max() <= 1e-5 * 80 + tol_v * float(rp[:, :3].abs().max())
-    if "node_pair" not in switch:                   # the weight fill changes no arithmetic at all: bit-identical
+    if set(switch) <= {"tma_fill", "coord_rows"}:   # the weight fill / the coordinate tile split change no arithmetic at all: bit-identical
         assert torch.equal(ap, rp) and torch.equal(ar, rr)
 
 
@@ -629,10 +633,15 @@ def test_frames_from_the_captured_loop_equal_the_host_driven_loop(prec):
     fp, fk = res[False][0], res[False][1]
     sp, sk = res[True][0], res[True][1]
     assert fp.shape == sp.shape == (4, int(g["counts"].sum()), 11) and fk.shape == sk.shape
-    tol = 1e-5 if prec == "fp32" else 1e-3
+    # The two paths differ in the LAST BIT of the schedule constants (the host table follows the reference's CPU op
+    # sequence, the per-step API evaluates the same torch ops on the device), which the sampler amplifies like any fp32
+    # rounding: the bound is relative to the coordinate scale the pocket is re-centred at (|z| ~ 690 here; the
+    # reference's own fp32-vs-fp64 difference on this fixture is 2.9e-4 = 4e-7 of it).
+    scale = max(1.0, float(sp[:, :, :3].abs().max()))
+    tol = (2e-6 if prec == "fp32" else 1e-4) * scale
     for idx in range(4):
-        assert (fp[idx] - sp[idx]).abs().max() <= tol * max(1.0, float(sp[idx].abs().max())), idx
-        assert (fk[idx] - sk[idx]).abs().max() <= tol * max(1.0, float(sk[idx].abs().max())), idx
+        assert (fp[idx] - sp[idx]).abs().max() <= tol, (idx, float((fp[idx] - sp[idx]).abs().max()), tol)
+        assert (fk[idx] - sk[idx]).abs().max() <= tol, (idx, float((fk[idx] - sk[idx]).abs().max()), tol)
     assert torch.equal(fk[1][:, 3:], fk[2][:, 3:])                        # pocket types are constant, un-normalised back to one-hot
     assert set(torch.unique(fk[1][:, 3:]).tolist()) <= {0.0, 1.0}
 
