@@ -148,7 +148,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
     if (const char* m = getenv("DIFFPHAR_COORD_ROWS")) h->coord_rows = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
-    if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "scan3") ? 3 : 0;
+    if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "fused") ? 4 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
         if (atoi(m)) {
             h->trace_kernel = atoi(m);
@@ -438,7 +438,8 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     p.use_cells = c.edge_cutoff > 0.f && p.max_nodes <= CELL_SAMPLE_MAX_NODES &&
                   (h->graph_mode == 2 || (h->graph_mode == 0 && p.max_nodes >= 512));
     // one-launch scan builder: a sample's candidates must fit 32 ballot chunks (two ranges, each rounded up to 32)
-    p.fused_graph = !p.use_cells && !p.seg_lanes && h->graph_mode != 3 && p.max_nodes <= 960;
+    // (DIFFPHAR_GRAPH=fused; OFF by default: measured 2 % slower per config-2 step than the three launches, graph.cu)
+    p.fused_graph = h->graph_mode == 4 && !p.use_cells && !p.seg_lanes && p.max_nodes <= 960;
     // One arena for every per-plan buffer: a layout that fits the arena re-carves it (no cudaMalloc / cudaFree, each of
     // which synchronises the device), so walking a pocket list re-plans in microseconds.
     Carver cv;
@@ -576,12 +577,22 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     const bool fp32_layout = h->precision == DP_FP32 || h->precision == DP_TF32 || !(h->tc_mask & 1);   // fp32 pq, 64-edge units
     const int unit = fp32_layout ? UNIT_F32 : UNIT_TC;
     int rc = 0;
-    if (!(h->skip_mask & 32) && (rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
-    // Fork: the radius graph (needs x only) runs on a side branch while the main branch projects the embedded
-    // features (needs h only); they join before the first edge kernel.  Works eagerly and under stream capture
+    // Fork: the radius graph (needs x only) runs on a side branch while the main branch encodes and projects the node
+    // features (need h only); they join before the first edge kernel.  Works eagerly and under stream capture
     // (the side stream joins the capture through the event).  Profiling spans need one stream: no fork then.
+    // In the sampler (pocket_base) the coordinates were already written by the previous DDPM update, so the branch
+    // starts BEFORE the encoder; a stand-alone evaluation gets them from the encoder and forks after it.
     const bool fork = !h->profile && !(h->skip_mask & 16);
-    if (fork) {
+    const bool early = fork && pocket_base && !(h->dbg & 32);             // dbg bit 5: fork after the encoder (A/B)
+    if (early) {
+        DP_CUDA(cudaEventRecord(h->ev_fork, st));
+        DP_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        if ((rc = launch_build_edges(h, p.x_in, h->side_stream))) return rc;
+        DP_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    }
+    if (!(h->skip_mask & 32) && (rc = launch_encode_nodes(h, xh_phar, xh_res, t_base, step_idx, row_stride, t_stride, pocket_base ? 2 : 0, st))) return rc;
+    if (early) {
+    } else if (fork) {
         DP_CUDA(cudaEventRecord(h->ev_fork, st));
         DP_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         if ((rc = launch_build_edges(h, p.x_in, h->side_stream))) return rc;
@@ -717,6 +728,7 @@ static int sampler_step_launches(dp_handle* h, float* pocket, const float* noise
     d.z = p.z; d.pocket = pocket; d.eps_hat = p.eps_hat; d.noise = noise;
     d.noise_step_stride = (int64_t)p.Np * PW; d.noise_step_base = 1;
     d.stat_base = 0; d.stat_index = -1; d.advance = 1;
+    d.x_in = p.x_in; d.x_a = p.x_a; d.x_b = p.x_b;                        // the next evaluation's coordinates
     if (fs.return_frames > 1) {
         d.frames_phar = fs.phar; d.frames_pocket = fs.pocket; d.return_frames = fs.return_frames; d.n_steps = h->n_steps;
         d.norm_x = fs.norm_x; d.norm_h = fs.norm_h; d.bias_h = fs.bias_h;
@@ -743,6 +755,7 @@ static int sample_core(dp_handle* h, const FrameSpec& fs, cudaStream_t st)
     DdpmArgs d0{};
     d0.kind = 2; d0.sigma = 1.0f; d0.z = p.z; d0.pocket = pocket; d0.eps_hat = nullptr; d0.noise = noise;
     d0.stat_index = -1; d0.advance = 0;
+    d0.x_in = p.x_in; d0.x_a = p.x_a; d0.x_b = p.x_b;
     if ((rc = launch_ddpm(h, d0, st))) return rc;
 
     if (h->profile) {

@@ -270,7 +270,7 @@ struct dp_handle {
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
     int graph_mode = 0;                // DIFFPHAR_GRAPH: 0 = auto (cell list for samples of >= 512 nodes), 1 = always scan, 2 = always cells,
-                                       // 3 = the three-launch scan (A/B of the one-launch builder)
+                                       // 4 = scan as ONE launch where it applies (count + look-back scan + fill; measured slower)
     int tc_mask = 3;                   // debug: bit 0 = edge kernels on tcgen05, bit 1 = node linears (DIFFPHAR_TC_MASK)
     bool has_weights = false;
     DeviceWeights w;
@@ -375,6 +375,9 @@ struct DdpmArgs {
     // un-normalised state (en_diffusion.py:891-906) to frame s * return_frames / n_steps when that division is exact
     float* frames_phar; float* frames_pocket; int return_frames; int n_steps;
     float norm_x, norm_h, bias_h;
+    // sampler: the update also writes the coordinates of the NEXT denoiser evaluation ([N][3] each: input frame + the two
+    // ping-pong copies), so that its radius graph can start before the encoder (null: the encoder writes them)
+    float* x_in; float* x_a; float* x_b;
 };
 int launch_ddpm(dp_handle* h, const DdpmArgs& a, cudaStream_t st);
 int launch_fill_noise(dp_handle* h, uint64_t seed, int n_draws, float* noise_dev, cudaStream_t st);

@@ -120,7 +120,12 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
     }
 }
 
-// ---- one-launch builder for small samples (Calpha pockets) ----------------------------------------
+// ---- one-launch builder for small samples (Calpha pockets), DIFFPHAR_GRAPH=fused, OFF by default --------------
+// Parity-green (bit-identical CSR, multi-wave grids included) but NOT faster: 337.6 vs 331.0 us per config-2 step against
+// the three launches on one box (profiles/r05e_ab_summary.txt).  All CTAs run at the same time here, so the prefix
+// has to propagate through the look-back window by window while hundreds of CTAs spin on acquire loads; the three
+// short launches the stream serialises for free are cheaper than that, and most of either hides beside the encoder and
+// the first projection anyway.  Kept as the measured answer to "fuse K1 into one launch".
 // count -> scan -> fill in ONE kernel: the three-launch version costs ~29 us at config-2 size (N = 10 k, 158 nodes per
 // sample), almost all of it launch latency and the single-CTA scan, and only ~10 us of it hide beside the first
 // projection.  Here a CTA owns 32 consecutive rows, one per warp (a first version with 8 rows per warp serialised

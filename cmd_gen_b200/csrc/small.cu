@@ -21,6 +21,7 @@ struct EncodeArgs {
     float* h; float* x_in; float* x_a; float* x_b;
     int* nan_flag;                                    // [0] cleared here: first kernel of every denoiser evaluation
     float* h_base; int base_mode;                     // see launch_encode_nodes
+    int skip_x;                                       // sampler (base_mode 2): x_in / x_a / x_b were written by the previous DDPM update
 };
 
 // One warp per node.  Every layer is out[o] = b[o] + sum_k in[k] w[k][o] with the outputs spread over
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
         // pocket node during sampling: features are constant, only the time column moves.  The time weight is the
         // LAST term of the reference's accumulation chain, so base + t * w_time is bit-identical to the full path.
         const float* src = a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
-        if (lane < 3) {
+        if (lane < 3 && !a.skip_x) {
             const float v = src[lane];
             a.x_in[3 * node + lane] = v; a.x_a[3 * node + lane] = v; a.x_b[3 * node + lane] = v;
         }
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) encode_nodes_kernel(EncodeArgs a)
     const float* src = phar ? a.xh_phar + (size_t)node * (3 + a.P) : a.xh_res + (size_t)(node - a.Np) * (3 + a.R);
     const float *w0 = phar ? a.pe0w : a.re0w, *b0 = phar ? a.pe0b : a.re0b;
     const float *w2 = phar ? a.pe2w : a.re2w, *b2 = phar ? a.pe2b : a.re2b;
-    if (lane < 3) {
+    if (lane < 3 && !a.skip_x) {
         const float v = src[lane];
         a.x_in[3 * node + lane] = v; a.x_a[3 * node + lane] = v; a.x_b[3 * node + lane] = v;
     }
@@ -313,6 +314,10 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
         float v = buf[idx];
         if (c < 3) v = __fsub_rn(v, mean[c]);
         d.z[(size_t)p0 * D + idx] = v;
+        if (d.x_in && c < 3) {                        // the next denoiser evaluation's coordinates (dynamics.py:77-81 clones them)
+            const size_t o = 3 * (size_t)(p0 + idx / D) + c;
+            d.x_in[o] = v; d.x_a[o] = v; d.x_b[o] = v;
+        }
         if (frame >= 0)                               // unnormalize_z, en_diffusion.py:891-906
             d.frames_phar[((size_t)frame * k.Np + p0) * D + idx] =
                 c < 3 ? __fmul_rn(v, d.norm_x) : __fadd_rn(__fmul_rn(v, d.norm_h), d.bias_h);
@@ -320,7 +325,12 @@ __global__ void __launch_bounds__(128) ddpm_kernel(DdpmKArgs k)
     for (int idx = tid; idx < nr * 3; idx += blockDim.x) {
         const int i = idx / 3, c = idx - 3 * i;
         float* px = d.pocket + (size_t)(r0 + i) * RW + c;
-        *px = __fsub_rn(*px, mean[c]);
+        const float v = __fsub_rn(*px, mean[c]);
+        *px = v;
+        if (d.x_in) {
+            const size_t o = 3 * (size_t)(k.Np + r0 + i) + c;
+            d.x_in[o] = v; d.x_a[o] = v; d.x_b[o] = v;
+        }
     }
     if (frame >= 0) {
         __syncthreads();                              // the translated coordinates of this sample's pocket rows
@@ -421,7 +431,7 @@ int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res,
     a.embw = w.emb.wt; a.embb = w.emb.b;
     a.h = p.h; a.x_in = p.x_in; a.x_a = p.x_a; a.x_b = p.x_b;
     const int grid = (p.N + 7) / 8;
-    a.nan_flag = p.nan_flag; a.h_base = p.h_base; a.base_mode = base_mode;
+    a.nan_flag = p.nan_flag; a.h_base = p.h_base; a.base_mode = base_mode; a.skip_x = base_mode == 2 ? 1 : 0;
     prof_begin(h, PROF_OTHER, st);
     DP_CUDA(launch_kernel(h->pdl, encode_nodes_kernel, dim3(grid), dim3(256), 0, st, a));
     prof_end(h, st);

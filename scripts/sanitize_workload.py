@@ -22,6 +22,7 @@ def main():
     tab = step_table(gamma_table("polynomial_2", 500, 1e-5), 500, 4)
     for prec in precisions:
         for seg, graph, sizes, counts, density in (("units", "scan", [40, 31], [5, 4], 0.0074),
+                                                   ("units", "fused", [40, 31], [5, 4], 0.0074),
                                                    ("lanes", "cells", [600, 530], [6, 3], 0.05)):
             os.environ["DIFFPHAR_SEG"], os.environ["DIFFPHAR_GRAPH"] = seg, graph
             h = _lib.Handle(cfg, "cuda:0", prec)

@@ -28,8 +28,8 @@ CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
 def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, coord_rows=None):
-    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "scan" takes
-    the one-launch kernel where it applies, "scan3" the three-launch version); coord_rows="1": the coordinate-mode edge kernel
+    """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "fused" = the scan
+    as one launch with a look-back prefix); coord_rows="1": the coordinate-mode edge kernel
     with row-owned tiles that finishes its rows itself;
     seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
     node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel."""
@@ -59,7 +59,7 @@ def csr_to_coo(rowptr, col):
 
 
 # ----------------------------------------------------------------------------- K1
-@pytest.mark.parametrize("graph", ["scan", "scan3", "cells"])
+@pytest.mark.parametrize("graph", ["scan", "fused", "cells"])
 @pytest.mark.parametrize("name", CASES)
 def test_edges_bit_exact_vs_reference(name, graph):
     g = load(f"dynamics_{name}.npz")
@@ -73,7 +73,7 @@ def test_edges_bit_exact_vs_reference(name, graph):
     assert np.array_equal((rowptr[1:] - rowptr[:-1]).cpu().numpy(), ref_deg)
 
 
-@pytest.mark.parametrize("graph", ["scan", "scan3", "cells"])
+@pytest.mark.parametrize("graph", ["scan", "fused", "cells"])
 @pytest.mark.parametrize("density,n_res,n_phar,B", [(0.0074, 150, 8, 64), (0.0074, 300, 10, 90), (0.05, 700, 12, 6), (0.05, 2000, 12, 3)])
 def test_edges_bit_exact_vs_oracle_medium(density, n_res, n_phar, B, graph):
     cfg = DynamicsConfig(residue_nf=20)
