@@ -99,6 +99,24 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t tmem_w,
     }
 }
 
+// The same tile product with A read from SHARED memory (SS form): used by a CTA that has exactly ONE tile — every CTA of
+// a coordinate-mode launch at Calpha size — where moving the 128 KB weight image on to tensor memory first
+// (32 tcgen05.cp at ~64 B/clk = 2 k cycles) would only delay the one tile that uses it.
+__device__ __forceinline__ void issue_tile_mma_ss(uint32_t tmem_d, const uint32_t (&w_panel)[4], uint32_t x_base, uint32_t idesc)
+{
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+        for (int ks = 0; ks < PANEL_K / 16; ++ks) {
+            const uint64_t bdesc = make_desc(x_base + kp * X_PANEL_BYTES + ks * 32);
+            const uint32_t acc = (kp > 0 || ks > 0) ? 1u : 0u;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+                umma_f16(tmem_d + hh * TILE, make_desc(w_panel[kp] + hh * (128 * 128) + ks * 32), bdesc, idesc, acc);
+        }
+    }
+}
+
 __device__ __forceinline__ void unpack8(const float4& a, const float4& b, float (&v)[8])
 {
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -226,6 +244,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const uint32_t tw = warp_uniform(tmem_w), td = warp_uniform(tmem_base);
             const uint32_t x0 = warp_uniform(smem_u32(s.x[0]));
             if (lane == 0) trace_mark(a.trace, 1, 63, 0);
+            const bool single = a.tma_fill && my_tiles == 1 && !(a.dbg & 64);   // one tile: SS-form MMAs straight from the landed image
+            const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
             if (a.tma_fill && my_tiles > 0) {
                 // Resident weights without the load / store units: four bulk copies bring the 128 KB image into the
                 // activation stages 1-3 and the gate-reduce buffer (all idle until the first tile is through), 32
@@ -233,7 +253,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 // MMAs), and the commit frees the buffers.  The producers' first loads no longer queue behind 16 warps
                 // of weight loads.
                 const uint32_t wl = smem_u32(&s.bar_wload);
-                const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
                 if (elect_one()) {
                     mbar_expect_tx(wl, 4 * W_PANEL_BYTES);
 #pragma unroll
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 __syncwarp();
                 mbar_wait(wl, 0);
                 tc_fence_after();
-                if (elect_one()) {
+                if (!single && elect_one()) {
 #pragma unroll
                     for (int kp = 0; kp < 4; ++kp)
 #pragma unroll
@@ -266,7 +285,8 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 if (lane == 0) trace_mark(a.trace, 1, it, 2);
                 tc_fence_after();
                 if (elect_one()) {
-                    issue_tile_mma(td + ts * TS_COLS, tw, x0 + xs * X_TILE_BYTES, idesc);
+                    if (single) issue_tile_mma_ss(td + ts * TS_COLS, dst, x0 + xs * X_TILE_BYTES, idesc);
+                    else issue_tile_mma(td + ts * TS_COLS, tw, x0 + xs * X_TILE_BYTES, idesc);
                     umma_commit(smem_u32(&s.bar_xempty[xs]));
                     umma_commit(smem_u32(&s.bar_tfull[ts]));
                 }
