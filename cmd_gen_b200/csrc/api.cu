@@ -447,7 +447,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.deg, p.N); cv.take(&p.rowptr, p.N + 1); cv.take(&p.agg_src, p.N);
     cv.take(&p.col, ecap); cv.take(&p.erow, ecap); cv.take(&p.edst, ecap); cv.take(&p.d0, ecap); cv.take(&p.escal, ecap);
     cv.take(&p.counts, 4);
-    cv.take(&p.scan_status, (size_t)p.N / 8 + 2);
+    cv.take(&p.scan_status, (size_t)p.N / 8 + 2); cv.take(&p.scan_ticket, 4);
     if (p.use_cells) {
         cv.take(&p.cell_start, (size_t)B * (CELLS_MAX + 1)); cv.take(&p.cell_nodes, p.N); cv.take(&p.cell_grid, (size_t)B * 8);
         p.bitmap_words = (p.max_nodes + 31) / 32;
@@ -469,6 +469,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     DP_CUDA(cudaMemcpy(p.sample_of, sample_of.data(), (size_t)p.N * sizeof(int), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(p.sample_ids, ids.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemset(p.counts, 0, 4 * sizeof(int)));
+    DP_CUDA(cudaMemset(p.scan_ticket, 0, 4 * sizeof(int)));                   // the count pass's arrival ticket (graph.cu)
     DP_CUDA(cudaMemset(p.nan_flag, 0, 4 * sizeof(int)));
     DP_CUDA(cudaMemset(p.step_idx, 0, sizeof(int)));
     DP_CUDA(cudaMemset(p.t_const, 0, 4 * sizeof(float)));

@@ -219,6 +219,7 @@ struct Plan {
     int bitmap_words = 0;        // ceil(max nodes per sample / 32)
     int fused_graph = 0;         // one-launch scan builder (graph.cu radius_rows_fused_kernel): small samples, units scheme
     unsigned long long* scan_status = nullptr;   // [ceil(N / 8)] look-back status words of that kernel
+    int* scan_ticket = nullptr;  // [4] arrival counter of the count pass: its last CTA runs the rowptr scan
     // node state
     float* h = nullptr;          // [N][H]
     float* h_base = nullptr;     // [Nr][H] sampler only: embedding of the (static) pocket features without the time term

@@ -31,7 +31,11 @@ struct GraphArgs {
     int* cell_start; int* cell_nodes; float* cell_grid;
     unsigned* row_bitmap; int bitmap_words;          // cells builder: the count pass keeps each row's hit bitmap for the fill pass
     unsigned long long* status;                      // fused builder: per-CTA scan status words (decoupled look-back), zeroed per build
+    int* ticket;                                     // count pass: arrival counter of the last-block scan (null: stand-alone scan kernel)
 };
+
+__device__ void scan_rowptr_block(const int* __restrict__ deg, int* __restrict__ rowptr, int N, int Np, int* counts, long long ecap);
+__device__ bool last_block_done(int* ticket);
 
 __device__ __forceinline__ float dist2_exact(float xi, float yi, float zi, float xj, float yj, float zj)
 {
@@ -118,6 +122,8 @@ __global__ void __launch_bounds__(256) radius_rows_kernel(GraphArgs a)
         }
         if (!FILL && lane == 0) a.deg[row] = found;
     }
+    if (!FILL && a.ticket && last_block_done(a.ticket))
+        scan_rowptr_block(a.deg, const_cast<int*>(a.rowptr), a.N, a.Np, a.counts, a.ecap);
 }
 
 // ---- one-launch builder for small samples (Calpha pockets), DIFFPHAR_GRAPH=fused, OFF by default --------------
@@ -458,23 +464,24 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
         if (!FILL && lane == 0) a.deg[row] = found;
         __syncwarp();
     }
+    if (!FILL && a.ticket && last_block_done(a.ticket))
+        scan_rowptr_block(a.deg, const_cast<int*>(a.rowptr), a.N, a.Np, a.counts, a.ecap);
 }
 
-// Exclusive scan of deg[N] -> rowptr[N+1] by one CTA: every thread owns 16 consecutive rows (four 128-bit
-// loads in flight), so 16 K rows take one block-wide scan step (N = 10 K: one step instead of ten).
-__global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict__ deg, int* __restrict__ rowptr,
-                                                          int N, int Np, int* counts, long long ecap)
+// Exclusive scan of deg[N] -> rowptr[N+1] by ONE CTA (any block size that is a multiple of 32, at most 1024): every
+// thread owns 16 consecutive rows (four 128-bit loads in flight).  Runs as the tail of the count pass: the CTA that
+// finishes counting LAST (atomic ticket, threadfence on both sides) scans — one launch (and its ~2.5 us of launch
+// latency on the critical side branch of every denoising step) less than a stand-alone scan kernel.
+__device__ void scan_rowptr_block(const int* __restrict__ deg, int* __restrict__ rowptr, int N, int Np, int* counts, long long ecap)
 {
     constexpr int PER = 16;
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    pdl_launch_dependents();
-    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
     if (tid == 0) carry_s = 0;
     const int cap = ecap < 2147483647LL ? (int)ecap : 2147483647;
     __syncthreads();
-    for (int base = 0; base < N; base += 1024 * PER) {
+    for (int base = 0; base < N; base += nthr * PER) {
         const int i0 = base + tid * PER;
         int v[PER];
         if (i0 + PER <= N && (N & 3) == 0) {
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
         if (lane == 31) warp_sums[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            int ws = warp_sums[lane];
+            int ws = lane < nwarp ? warp_sums[lane] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int n = __shfl_up_sync(0xffffffffu, ws, o);
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
             run += v[q];
         }
         __syncthreads();
-        if (tid == 1023) carry_s = carry + warp_sums[31];
+        if (tid == nthr - 1) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
     // Overflow (more edges than the plan's capacity): every consumer indexes the per-edge arrays by rowptr / counts,
@@ -526,10 +533,35 @@ __global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict
         const int E = carry_s;
         rowptr[N] = E < cap ? E : cap;
         counts[0] = E < cap ? E : cap;
-        if ((long long)E > ecap) counts[2] = E;
+        if ((long long)E > ecap && E > counts[2]) counts[2] = E;
     }
     __syncthreads();
     if (tid == 0) counts[1] = rowptr[Np];   // E_p: rows [0, Np) are the phar nodes (clamped like every rowptr entry)
+}
+
+// the count pass's tail: true in exactly one CTA, after every CTA's deg[] stores are visible to it
+__device__ bool last_block_done(int* ticket)
+{
+    __shared__ int is_last_s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        is_last_s = t == (int)gridDim.x - 1;
+        if (is_last_s) *ticket = 0;                                      // ready for the next build
+    }
+    __syncthreads();
+    const bool last = is_last_s != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+__global__ void __launch_bounds__(1024) scan_rowptr_kernel(const int* __restrict__ deg, int* __restrict__ rowptr,
+                                                          int N, int Np, int* counts, long long ecap)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    scan_rowptr_block(deg, rowptr, N, Np, counts, ecap);
 }
 
 }  // namespace
@@ -546,6 +578,8 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     a.cell_start = p.cell_start; a.cell_nodes = p.cell_nodes; a.cell_grid = p.cell_grid;
     a.row_bitmap = p.row_bitmap; a.bitmap_words = p.bitmap_words;
     a.status = p.scan_status;
+    const bool tail_scan = !(h->dbg & 128);                              // dbg bit 7: stand-alone scan kernel (A/B)
+    a.ticket = tail_scan ? p.scan_ticket : nullptr;                      // zeroed at plan time, reset by the block that scans
     const int wpb = 8;
     int grid = (p.N + wpb - 1) / wpb;
     const int max_grid = h->sm_count * 16;
@@ -561,9 +595,9 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
     if (p.use_cells) {
         DP_CUDA(launch_kernel(h->pdl, cell_build_kernel, dim3(p.B), dim3(256), 0, st, a));
         DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<false>, dim3(grid), dim3(256), 0, st, a));
-        DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
+        if (!tail_scan) DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
         DP_CUDA(launch_kernel(h->pdl, radius_cells_kernel<true>, dim3(grid), dim3(256), 0, st, a));
-        h->launches += 1;
+        h->launches += tail_scan ? 0 : 1;
     } else if (p.fused_graph) {
         // one launch (+ the status clear): see radius_rows_fused_kernel
         const int n_cta = (p.N + FUSED_ROWS - 1) / FUSED_ROWS;
@@ -572,8 +606,9 @@ int launch_build_edges(dp_handle* h, const float* x_dev, cudaStream_t st)
         h->launches -= 2;
     } else {
         DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<false>, dim3(grid), dim3(256), 0, st, a));
-        DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
+        if (!tail_scan) DP_CUDA(launch_kernel(h->pdl, scan_rowptr_kernel, dim3(1), dim3(1024), 0, st, (const int*)p.deg, p.rowptr, p.N, p.Np, p.counts, (long long)p.Ecap));
         DP_CUDA(launch_kernel(h->pdl, radius_rows_kernel<true>, dim3(grid), dim3(256), 0, st, a));
+        if (tail_scan) h->launches -= 1;
     }
     prof_end(h, st);
     h->launches += 3;

@@ -99,9 +99,8 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t tmem_w,
     }
 }
 
-// The same tile product with A read from SHARED memory (SS form): used by a CTA that has exactly ONE tile — every CTA of
-// a coordinate-mode launch at Calpha size — where moving the 128 KB weight image on to tensor memory first
-// (32 tcgen05.cp at ~64 B/clk = 2 k cycles) would only delay the one tile that uses it.
+// The same tile product with A read from SHARED memory (SS form), for a CTA that has exactly ONE tile (every CTA of a
+// coordinate-mode launch at Calpha size): an experiment (DIFFPHAR_DBG bit 6), measured slower than the resident path.
 __device__ __forceinline__ void issue_tile_mma_ss(uint32_t tmem_d, const uint32_t (&w_panel)[4], uint32_t x_base, uint32_t idesc)
 {
 #pragma unroll
@@ -244,7 +243,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const uint32_t tw = warp_uniform(tmem_w), td = warp_uniform(tmem_base);
             const uint32_t x0 = warp_uniform(smem_u32(s.x[0]));
             if (lane == 0) trace_mark(a.trace, 1, 63, 0);
-            const bool single = a.tma_fill && my_tiles == 1 && !(a.dbg & 64);   // one tile: SS-form MMAs straight from the landed image
+            // dbg bit 6: a CTA with ONE tile issues SS-form MMAs straight from the landed image.  Measured negative
+            // (profiles/r05i_ab_summary.txt: 337 vs 331 us per config-2 step): the tcgen05.cp detour overlaps the producers'
+            // first gathers, the SS MMAs then read 6 KB instead of 2 KB each through the ~64-80 B/clk operand port.
+            const bool single = a.tma_fill && my_tiles == 1 && (a.dbg & 64);
             const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
             if (a.tma_fill && my_tiles > 0) {
                 // Resident weights without the load / store units: four bulk copies bring the 128 KB image into the
