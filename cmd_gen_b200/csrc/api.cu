@@ -146,7 +146,6 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_TMA_FILL")) h->tma_fill = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
-    if (const char* m = getenv("DIFFPHAR_COORD_ROWS")) h->coord_rows = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "fused") ? 4 : 0;
     if (const char* m = getenv("DIFFPHAR_TRACE")) {
@@ -661,18 +660,13 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr; q.range_flag = p.nan_flag + 2;
-            q.coord_rows = h->coord_rows;              // DIFFPHAR_COORD_ROWS=1: row-owned tiles + in-kernel finish (measured slower, see tc_edge.cu)
-            q.x_next = x_next; q.norm_constant = c.norm_constant; q.coords_range = c.coords_range;
-            q.norm_factor = c.normalization_factor; q.mean = c.aggregation_mean;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
-            // the tcgen05 kernel finishes its own phar rows (tc_edge.cu, coordinate mode); the FFMA path runs the stand-alone finish
-            const bool fused_finish = !fp32_layout && q.coord_rows && !(h->dbg & 8);
-            if (!fused_finish) {
-                prof_begin(h, PROF_EDGE_COORD, st);
-                rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
-                prof_end(h, st);
-                if (rc) return rc;
-            }
+            // (a coordinate-mode kernel with row-owned tiles that finishes its phar rows itself — no second launch — was built,
+            //  parity-green, and measured 5 % SLOWER per step; commit 5e2a79c, profiles/r05e_ab_summary.txt)
+            prof_begin(h, PROF_EDGE_COORD, st);
+            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
+            prof_end(h, st);
+            if (rc) return rc;
             float* t = x_cur; x_cur = x_next; x_next = t;
         }
     }

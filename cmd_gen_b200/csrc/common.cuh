@@ -263,8 +263,6 @@ struct dp_handle {
     int sm_count = 148;
     int precision = 0;
     int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
-    int coord_rows = 0;                // DIFFPHAR_COORD_ROWS=1: coordinate-mode edge kernel with row-owned tiles that finishes its rows itself
-                                       // (one launch less per block, but measured 6 % slower per step: profiles/r05c_ab_summary.txt)
     int seg_mode = 0;                  // DIFFPHAR_SEG: 0 automatic, 1 units, 2 lanes (Plan::seg_lanes)
     int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
     int tma_fill = 1;                  // DIFFPHAR_TMA_FILL=0: resident weights through LDG + tcgen05.st (A/B; EdgeArgs::tma_fill)
@@ -345,10 +343,7 @@ struct EdgeArgs {
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)
-    float* x_next;                                   // coord == 1, tcgen05 path: the kernel finishes the phar rows itself (x + masked row sum)
-    float norm_constant, coords_range, norm_factor; int mean;   // ... with these (coord2diff, egnn_new.py:91, 283-291)
     int coord; int attention; int use_tanh;
-    int coord_rows;                                  // coord == 1, tcgen05 path: every CTA owns a contiguous range of phar rows (tc_edge.cu)
     long long* trace;                                // debug timeline (dp_debug_trace), normally null
     int* range_flag;                                 // tcgen05 path: sticky f16-range bits (Plan::nan_flag + 2)
 };

@@ -59,8 +59,8 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
-constexpr int REGS_MMA = 32;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless,
-                                                  // and the 8 spare registers keep the producers' setmaxnreg.inc from waiting on every dec
+constexpr int REGS_MMA = 32;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless;
+                                                  // 40 (no spill) left the producers' setmaxnreg.inc no slack and measured no faster
 #ifndef EDGE_REGS_PACKED_PRODUCER
 #define EDGE_REGS_PACKED_PRODUCER 104
 #define EDGE_REGS_PACKED_EPILOGUE 64
@@ -95,23 +95,6 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t tmem_d, uint32_t tmem_w,
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
                 umma_f16_ts(tmem_d + hh * TILE, tmem_w + hh * 128 + kp * 32 + ks * 8, bdesc, idesc, acc);
-        }
-    }
-}
-
-// The same tile product with A read from SHARED memory (SS form), for a CTA that has exactly ONE tile (every CTA of a
-// coordinate-mode launch at Calpha size): an experiment (DIFFPHAR_DBG bit 6), measured slower than the resident path.
-__device__ __forceinline__ void issue_tile_mma_ss(uint32_t tmem_d, const uint32_t (&w_panel)[4], uint32_t x_base, uint32_t idesc)
-{
-#pragma unroll
-    for (int kp = 0; kp < 4; ++kp) {
-#pragma unroll
-        for (int ks = 0; ks < PANEL_K / 16; ++ks) {
-            const uint64_t bdesc = make_desc(x_base + kp * X_PANEL_BYTES + ks * 32);
-            const uint32_t acc = (kp > 0 || ks > 0) ? 1u : 0u;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-                umma_f16(tmem_d + hh * TILE, make_desc(w_panel[kp] + hh * (128 * 128) + ks * 32), bdesc, idesc, acc);
         }
     }
 }
@@ -153,23 +136,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     int s_row = 0, s_col = 0; float s_d0 = 0.f;
-    const bool crow = a.coord && a.coord_rows;           // coordinate mode with row-owned tiles (default); else the message-mode split
-    if (!crow && !a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
+    if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
-    // Coordinate mode with row-owned tiles (EdgeArgs::coord_rows, DIFFPHAR_COORD_ROWS=1; OFF by default): the CTA OWNS a
-    // contiguous range of phar rows [c_r0, c_r1) — hence a contiguous CSR edge range [c_e0, c_e1) — so that after its
-    // tiles it can finish those rows itself (coord_diff * scalar, row sum, x update: egnn_new.py:91-103) without any
-    // cross-CTA dependency: no second launch.  Parity-green, but measured SLOWER on one box (profiles/r05c_ab_summary.txt:
-    // 356 vs 336 us per config-2 step): the split costs two more dependent L2 round trips before the first gather (rowptr,
-    // then metadata that can no longer be requested speculatively at kernel entry) and wakes all 148 CTAs for the 128 KB
-    // weight fill instead of 94; fusing the finish recovers only 7 of those 27 us.  The default keeps the message-mode
-    // tile split and the stand-alone coord_finish_kernel.
-    const int c_r0 = crow ? (int)((long long)blockIdx.x * a.n_moving / (int)gridDim.x) : 0;
-    const int c_r1 = crow ? (int)((long long)(blockIdx.x + 1) * a.n_moving / (int)gridDim.x) : 0;
-    const int c_e0 = crow ? a.rowptr[c_r0] : 0, c_e1 = crow ? a.rowptr[c_r1] : 0;
-    const int E = crow ? c_e1 : *a.n_edges;                  // exclusive end of the edges this CTA may touch
+    const int E = *a.n_edges;
 
     // ---- prologue
     if (tid == 0) {
@@ -222,16 +193,12 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     // for every CTA that has a long lane and one (empty, skipped by has_unit) tile too many for the others — which
     // finish no later than the CTAs that need it.  Idle CTAs fall through with 0.
     int my_tiles;
-    if (crow) my_tiles = (c_e1 - c_e0 + TILE - 1) / TILE;
-    else if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
+    if (a.contig) my_tiles = lane_first_unit(4u * blockIdx.x + 4u, U, L) > lane_first_unit(4u * blockIdx.x, U, L) ? (int)((U + L - 1u) / L) : 0;
     else my_tiles = max(0, ((E + TILE - 1) / TILE - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
-    // group g's 16 edges of tile `it` start at edge_base(g) + it * edge_step, and exist while it < unit_count(g)
-    //   coordinate mode: tiles are 64 consecutive edges from the CTA's first edge (any alignment: nothing is keyed on units)
-    const bool lanes = a.contig && !crow;
-    const int edge_step = crow ? TILE : (lanes ? UNIT_TC : TILE * (int)gridDim.x);
-    auto unit_base = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
-    auto edge_base = [&](int g) { return crow ? c_e0 + UNIT_TC * g : UNIT_TC * unit_base(g); };
-    auto unit_count = [&](int g) { return lanes ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
+    // group g's unit of tile `it` is unit_base(g) + it * unit_step, and exists while it < unit_count(g)
+    const int unit_step = a.contig ? 1 : 4 * (int)gridDim.x;
+    auto unit_base = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g, U, L) : 4 * (int)blockIdx.x + g; };
+    auto unit_count = [&](int g) { return a.contig ? (int)lane_first_unit(4u * blockIdx.x + g + 1u, U, L) - unit_base(g) : my_tiles; };
 
     if (wid >= MMA_WARP) {
         // ================================ MMA issuer ================================
@@ -243,11 +210,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const uint32_t tw = warp_uniform(tmem_w), td = warp_uniform(tmem_base);
             const uint32_t x0 = warp_uniform(smem_u32(s.x[0]));
             if (lane == 0) trace_mark(a.trace, 1, 63, 0);
-            // dbg bit 6: a CTA with ONE tile issues SS-form MMAs straight from the landed image.  Measured negative
-            // (profiles/r05i_ab_summary.txt: 337 vs 331 us per config-2 step): the tcgen05.cp detour overlaps the producers'
-            // first gathers, the SS MMAs then read 6 KB instead of 2 KB each through the ~64-80 B/clk operand port.
-            const bool single = a.tma_fill && my_tiles == 1 && (a.dbg & 64);
-            const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
             if (a.tma_fill && my_tiles > 0) {
                 // Resident weights without the load / store units: four bulk copies bring the 128 KB image into the
                 // activation stages 1-3 and the gate-reduce buffer (all idle until the first tile is through), 32
@@ -255,6 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 // MMAs), and the commit frees the buffers.  The producers' first loads no longer queue behind 16 warps
                 // of weight loads.
                 const uint32_t wl = smem_u32(&s.bar_wload);
+                const uint32_t dst[4] = {x0 + 1 * X_TILE_BYTES, x0 + 2 * X_TILE_BYTES, x0 + 3 * X_TILE_BYTES, warp_uniform(smem_u32(s.red))};
                 if (elect_one()) {
                     mbar_expect_tx(wl, 4 * W_PANEL_BYTES);
 #pragma unroll
@@ -263,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 __syncwarp();
                 mbar_wait(wl, 0);
                 tc_fence_after();
-                if (!single && elect_one()) {
+                if (elect_one()) {
 #pragma unroll
                     for (int kp = 0; kp < 4; ++kp)
 #pragma unroll
@@ -287,8 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 if (lane == 0) trace_mark(a.trace, 1, it, 2);
                 tc_fence_after();
                 if (elect_one()) {
-                    if (single) issue_tile_mma_ss(td + ts * TS_COLS, dst, x0 + xs * X_TILE_BYTES, idesc);
-                    else issue_tile_mma(td + ts * TS_COLS, tw, x0 + xs * X_TILE_BYTES, idesc);
+                    issue_tile_mma(td + ts * TS_COLS, tw, x0 + xs * X_TILE_BYTES, idesc);
                     umma_commit(smem_u32(&s.bar_xempty[xs]));
                     umma_commit(smem_u32(&s.bar_tfull[ts]));
                 }
@@ -311,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_producer(MODE)));
         const int pw = wid - EPI_WARPS;
-        const int ebase = edge_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
+        const int unit0 = unit_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
         const int e_off = 8 * (pw & 1) + lane;                                           // its half of the unit's 16 edges
         float wr[8], wd[8];
         unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
@@ -332,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         // Slots without an edge (past E, or past the end of a shorter lane) are processed as edge (0, 0): finite garbage in columns nobody reads.
         int m_row = 0, m_col = 0; float m_r2 = 0.f, m_d0 = 0.f;
         auto load_rc = [&](int it, int& r, int& c, float& d0) {
-            const int e = ebase + it * edge_step + e_off;
+            const int e = (unit0 + it * unit_step) * UNIT_TC + e_off;
             r = 0; c = 0; d0 = 0.f;
             if (it < n_units && lane < 8 && e < E) { r = a.erow[e]; c = a.ecol[e]; d0 = a.d0[e]; }
         };
@@ -342,10 +304,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // coord2diff, egnn_new.py:265-268
         };
         int n_row, n_col; float n_d0;
-        if (a.contig || crow) {
+        if (a.contig) {
             load_rc(0, m_row, m_col, m_d0);
         } else {
-            const bool ok = my_tiles > 0 && lane < 8 && ebase + e_off < E;                 // the speculative loads were real edges
+            const bool ok = my_tiles > 0 && lane < 8 && unit0 * UNIT_TC + e_off < E;       // the speculative loads were real edges
             m_row = ok ? s_row : 0; m_col = ok ? s_col : 0; m_d0 = ok ? s_d0 : 0.f;
         }
         uint4 pb[8];
@@ -364,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
         const int l74 = (lane & 7) << 4;
 
-        bool range_bad = false;
+        float rd_max = 0.f;                                                              // largest r2 / d0 packed to f16 (range guard)
         for (int it = 0; it < my_tiles; ++it) {
             const int xs = it % N_XS;
             int f_row, f_col; float f_d0;
@@ -383,9 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             if (PACKED) {                                                               // (r2, d0) of the lane's edge as one f16x2 word
                 const __half2 t = __floats2half2_rn(fminf(m_r2, 60000.f), fminf(m_d0, 60000.f));
                 m_rd = *reinterpret_cast<const uint32_t*>(&t);
-                // beyond f16's range the clamp makes this edge differ from the reference (only reachable without a cutoff):
-                // flagged, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
-                range_bad |= fmaxf(m_r2, m_d0) > 60000.f;                                    // reported once, after the tile loop
+                rd_max = fmaxf(rd_max, fmaxf(m_r2, m_d0));
             }
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
@@ -452,7 +412,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             m_r2 = n_moving ? dist2(xr0, xr1, xr2, xc0, xc1, xc2) : n_d0;
             n_row = f_row; n_col = f_col; n_d0 = f_d0;
         }
-        if (range_bad) atomicOr(a.range_flag, 2);
+        // beyond f16's range the clamp above makes an edge differ from the reference (only reachable without a cutoff):
+        // flagged once per launch, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
+        if (rd_max > 60000.f) atomicOr(a.range_flag, 2);
     } else {
         // ================================ epilogue ================================
         if (regs_epilogue(MODE) > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));
@@ -469,11 +431,11 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         float* gatew = s.gate[ew];
         const int l16 = lane & 15, g16 = lane >> 4;
         if (!a.tma_fill && my_tiles > 0) fill_weights();
-        const int ebase = edge_base(gi), n_units = unit_count(gi);                      // this group's units
+        const int unit0 = unit_base(gi), n_units = unit_count(gi);                      // this group's units
         float s0 = 0.f, s1 = 0.f;                                                        // running sum of the current CSR row: carried across tiles
         for (int it = 0; it < my_tiles; ++it) {
             const int ts = it % N_TS;
-            const int u0 = ebase + it * edge_step;                                       // first edge of this group's unit
+            const int u0 = (unit0 + it * unit_step) * UNIT_TC;                           // first edge of this group's unit
             const bool has_unit = it < n_units;                                          // shorter lanes idle through the CTA's last tile
             const int my_dst = (!a.coord && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
@@ -564,42 +526,6 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 __syncwarp();                                                            // gatew / redw are rewritten next tile
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 7);
-        }
-        if (crow && !(a.dbg & 8)) {                                                      // dbg bit 3: A/B against the stand-alone finish launch
-            // ---- finish the CTA's own phar rows (replaces coord_finish_kernel): eight lanes per row, lane l takes the row's
-            // edges l, l + 8, ... in CSR order, a fixed-order shuffle tree combines them — deterministic, no atomics, the
-            // same arithmetic in the same order as the stand-alone kernel (small.cu) the FFMA path still launches.
-            named_bar_sync(1 + EPI_GROUPS, EPI_WARPS * 32);                              // every scalar of this CTA's rows is written
-            const int l = tid & 7;
-            for (int rb = c_r0; rb < c_r1; rb += EPI_WARPS * 4) {
-                const int r = rb + (tid >> 3);
-                const bool live = r < c_r1;
-                const int rs = live ? a.rowptr[r] : 0, re = live ? a.rowptr[r + 1] : 0;
-                const float xi = live ? a.x[3 * r] : 0.f, yi = live ? a.x[3 * r + 1] : 0.f, zi = live ? a.x[3 * r + 2] : 0.f;
-                float sx = 0.f, sy = 0.f, sz = 0.f;
-                for (int k = rs + l; k < re; k += 8) {
-                    const int j = a.ecol[k];
-                    const float dx = xi - a.x[3 * j], dy = yi - a.x[3 * j + 1], dz = zi - a.x[3 * j + 2];
-                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                    const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(r2, 1e-8f)), a.norm_constant);    // coord2diff, egnn_new.py:269-270
-                    const float v = a.escal[k];
-                    float tx = __fmul_rn(__fdiv_rn(dx, nrm), v), ty = __fmul_rn(__fdiv_rn(dy, nrm), v), tz = __fmul_rn(__fdiv_rn(dz, nrm), v);
-                    if (a.use_tanh) { tx = __fmul_rn(tx, a.coords_range); ty = __fmul_rn(ty, a.coords_range); tz = __fmul_rn(tz, a.coords_range); }
-                    sx = __fadd_rn(sx, tx); sy = __fadd_rn(sy, ty); sz = __fadd_rn(sz, tz);
-                }
-#pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
-                    sx = __fadd_rn(sx, __shfl_down_sync(0xffffffffu, sx, o, 8));
-                    sy = __fadd_rn(sy, __shfl_down_sync(0xffffffffu, sy, o, 8));
-                    sz = __fadd_rn(sz, __shfl_down_sync(0xffffffffu, sz, o, 8));
-                }
-                if (live && l == 0) {
-                    const float d = a.mean ? (float)max(re - rs, 1) : a.norm_factor;             // egnn_new.py:283-291
-                    a.x_next[3 * r] = __fadd_rn(xi, __fdiv_rn(sx, d));
-                    a.x_next[3 * r + 1] = __fadd_rn(yi, __fdiv_rn(sy, d));
-                    a.x_next[3 * r + 2] = __fadd_rn(zi, __fdiv_rn(sz, d));
-                }
-            }
         }
     }
     tc_fence_before();

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 900 python bench.py --steps 10 --warmup 3 --sweep ${SWEEP:-16,64} > $OUT/${TAG}_bench_f16fast.json 2> $OUT/${TAG}_bench_f16fast.err
 cat $OUT/${TAG}_bench_f16fast.json; tail -3 $OUT/${TAG}_bench_f16fast.err
 # same-box A/B (5 runs each): stand-alone coord finish launch; three-launch graph builder
-for V in ${AB_SET:-"base:" "scan_kernel_standalone:DIFFPHAR_DBG=128" "base_again:" "scan_kernel_standalone_again:DIFFPHAR_DBG=128" "single_tile_ss:DIFFPHAR_DBG=64" "skip_coord:DIFFPHAR_SKIP=12" "skip_node:DIFFPHAR_SKIP=2"}; do
+for V in ${AB_SET:-"base:" "scan_kernel_standalone:DIFFPHAR_DBG=128" "base_again:" "scan_kernel_standalone_again:DIFFPHAR_DBG=128" "skip_coord:DIFFPHAR_SKIP=12" "skip_node:DIFFPHAR_SKIP=2"}; do
   NAME=${V%%:*}; ENVV=${V#*:}
   env $ENVV timeout 300 python bench.py --steps 5 --warmup 3 --no-also --no-cpu-baseline > $OUT/${TAG}_ab_${NAME}.json 2> $OUT/${TAG}_ab_${NAME}.err
   python - <<PY

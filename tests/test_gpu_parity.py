@@ -27,15 +27,13 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, coord_rows=None):
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None):
     """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "fused" = the scan
-    as one launch with a look-back prefix); coord_rows="1": the coordinate-mode edge kernel
-    with row-owned tiles that finishes its rows itself;
+    as one launch with a look-back prefix);
     seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
     node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel."""
     import os
-    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill,
-              "DIFFPHAR_COORD_ROWS": coord_rows}
+    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill}
     old = {k: os.environ.pop(k, None) for k in forced}
     for k, v in forced.items():
         if v:
@@ -288,8 +286,7 @@ def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg)
         assert torch.equal(a2.cpu(), a) and torch.equal(r2.cpu(), r)
 
 
-@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}, {"coord_rows": "1"},
-                                    {"coord_rows": "1", "seg": "lanes"}])
+@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}])
 def test_alternative_kernel_paths_match_the_default(switch):
     """The switchable kernel variants kept for A/B runs (CTA-pair node kernel with tcgen05 cta_group::2 and DSMEM bulk
     exchange; LDG + tcgen05.st weight fill of the edge kernel) against the default path on a ragged batch: same
@@ -315,7 +312,7 @@ def test_alternative_kernel_paths_match_the_default(switch):
     assert (ap[:, 3:] - rp[:, 3:]).abs().max() <= tol_h * max(1.0, float(rp[:, 3:].abs().max()))
     assert (ar[:, 3:] - rr[:, 3:]).abs().max() <= tol_h * max(1.0, float(rr[:, 3:].abs().max()))
     assert (ap[:, :3] - rp[:, :3]).abs().max() <= 1e-5 * 80 + tol_v * float(rp[:, :3].abs().max())
-    if set(switch) <= {"tma_fill", "coord_rows"}:   # the weight fill / the coordinate tile split change no arithmetic at all: bit-identical
+    if set(switch) <= {"tma_fill"}:                 # the weight fill changes no arithmetic at all: bit-identical
         assert torch.equal(ap, rp) and torch.equal(ar, rr)
 
 
