@@ -381,8 +381,10 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
 {
     __shared__ unsigned bitmap_s[8][CELL_SAMPLE_MAX_NODES / 32];
+    __shared__ int rng_s[8][2][12];                  // per warp: prefix sums / first entries of the row's 9 candidate ranges
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned* bm = bitmap_s[wid];
+    int (*rng)[12] = rng_s[wid];
     pdl_launch_dependents();
     pdl_wait();
     for (int row = blockIdx.x * 8 + wid; row < a.N; row += gridDim.x * 8) {
@@ -404,23 +406,54 @@ __global__ void __launch_bounds__(256) radius_cells_kernel(GraphArgs a)
         const int nx = dims & 255, ny = (dims >> 8) & 255, nz = dims >> 16;
         const int cx = cell_coord(xi, g[0], g[3], nx), cy = cell_coord(yi, g[1], g[4], ny), cz = cell_coord(zi, g[2], g[5], nz);
         const int* cs = a.cell_start + (size_t)b * (CELLS_MAX + 1);
-        for (int dz = -1; dz <= 1; ++dz) {
-            const int z = cz + dz;
-            if (z < 0 || z >= nz) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int y = cy + dy;
-                if (y < 0 || y >= ny) continue;
-                // the x-neighbours are consecutive buckets: one contiguous candidate range per (y, z)
+        // The 27 neighbouring buckets are 9 contiguous candidate ranges (the x-neighbours are consecutive buckets: one
+        // range per (y, z)).  Walking them one after the other costs three DEPENDENT L2 round trips per range (bounds ->
+        // bucket entry -> coordinates), 27 per row — the pass was latency-bound at ~220 us for config 3.  Instead: lanes
+        // 0..8 fetch the 9 range bounds together, a warp scan flattens the ranges into one candidate list (~300 entries at
+        // full-atom density), and every lane takes 8 candidates per batch with all their bucket loads, then all their
+        // coordinate loads, in flight at once: ~3 round trips per batch, one or two batches per row.
+        int r_lo = 0, r_len = 0;
+        if (lane < 9) {
+            const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
+            if (z >= 0 && z < nz && y >= 0 && y < ny) {
                 const int c_lo = (z * ny + y) * nx + (cx > 0 ? cx - 1 : 0);
                 const int c_hi = (z * ny + y) * nx + (cx + 1 < nx ? cx + 1 : nx - 1);
-                const int k_end = cs[c_hi + 1];
-                for (int k = cs[c_lo] + lane; k < k_end; k += 32) {
-                    const int j = a.cell_nodes[k];
-                    const float d2 = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
-                    if (__fsqrt_rn(d2) <= a.cutoff) {
-                        const int loc = j < a.Np ? j - p0 : np + (j - r0);
-                        atomicOr(&bm[loc >> 5], 1u << (loc & 31));
-                    }
+                r_lo = cs[c_lo];
+                r_len = cs[c_hi + 1] - r_lo;
+            }
+        }
+        int incl = r_len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 8);
+        if (lane < 9) { rng[0][lane + 1] = incl; rng[1][lane] = r_lo; }
+        if (lane == 0) rng[0][0] = 0;
+        __syncwarp();
+        constexpr int CB = 8;                                                    // candidates per lane and batch
+        for (int c0 = 0; c0 < total; c0 += 32 * CB) {
+            int jj[CB];
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+                const int c = c0 + 32 * q + lane;
+                jj[q] = -1;
+                if (c < total) {
+                    int r = 0;
+                    while (c >= rng[0][r + 1]) ++r;                              // at most 8 steps over the 9 prefix sums
+                    jj[q] = a.cell_nodes[rng[1][r] + (c - rng[0][r])];
+                }
+            }
+            float d2[CB];
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+                const int j = jj[q] >= 0 ? jj[q] : row;
+                d2[q] = dist2_exact(xi, yi, zi, a.x[3 * j], a.x[3 * j + 1], a.x[3 * j + 2]);
+            }
+#pragma unroll
+            for (int q = 0; q < CB; ++q) {
+                if (jj[q] >= 0 && __fsqrt_rn(d2[q]) <= a.cutoff) {
+                    const int j = jj[q];
+                    const int loc = j < a.Np ? j - p0 : np + (j - r0);
+                    atomicOr(&bm[loc >> 5], 1u << (loc & 31));
                 }
             }
         }
