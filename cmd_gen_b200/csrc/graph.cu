@@ -303,8 +303,13 @@ __global__ void __launch_bounds__(256) cell_build_kernel(GraphArgs a)
     const int r0 = a.Np + a.res_off[b], nr = a.res_off[b + 1] - a.res_off[b];
     const int n = np + nr;
     auto node_of = [&](int i) { return i < np ? p0 + i : r0 + (i - np); };
+    // The grid spans the POCKET nodes only (all nodes when the sample has none): pharmacophore points may sit far outside
+    // it — with random-init weights they drift to |x| ~ 1000 A — and a bounding box over them would blow the 16 x 16 x 16
+    // cell budget up to cells of > 100 A, i.e. every row tests the whole sample (measured: 5 000 warp instructions per row,
+    // 230 us per count pass at config 3).  Points outside the box are clamped into the boundary cells by cell_coord,
+    // which stays monotone, so neighbours within the cutoff still differ by at most one cell per axis.
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid + (nr > 0 ? np : 0); i < n; i += 256) {
         const int j = node_of(i);
 #pragma unroll
         for (int d = 0; d < 3; ++d) { const float v = a.x[3 * j + d]; mn[d] = fminf(mn[d], v); mx[d] = fmaxf(mx[d], v); }

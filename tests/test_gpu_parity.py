@@ -109,6 +109,8 @@ def test_edges_cells_equal_scan_at_config_sizes(n_res, n_phar, B, density):
     if xp.shape[0] > 3:
         xp[1] = xp[0]                                                 # coincident points
         xp[2] = pocket["x"][5]                                        # a phar point on top of a residue of its own sample
+        xp[3] = xp[3] * 40.0                                          # ~1 000 A away: far outside the pocket's cell grid (clamped into a boundary cell)
+        xp[-1] = pocket["x"][-1] + torch.tensor([5.0, 0.0, 0.0])      # just outside the box, within the cutoff of a boundary atom
     x = torch.cat([xp, pocket["x"]]).to(DEV)
     out = {}
     for graph in ("scan", "cells"):
