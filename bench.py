@@ -567,6 +567,25 @@ def run_ours(args, rank, world, local_rank):
                 also.append(side_workload(name, dev, args.precision, flush))
             except Exception as ex:
                 also.append({"workload": WORKLOADS[name]["label"], "error": repr(ex)[:300]})
+        # ---- the other arithmetic modes on the same batch (two timed runs each; f16fast is the headline) --------------
+        try:
+            modes = {}
+            for prec in ("bf16", "f16", "tf32"):
+                if prec == args.precision:
+                    continue
+                hp = _lib.Handle(cfg, dev, prec)
+                hp.set_weights(pack_blob(cfg, init_weights(cfg, 0)))
+                hp.plan(counts, [WORKLOAD["n_res"]] * B)
+                hp.set_step_table(tab.rows, tab.final)
+                ms = timed_runs(lambda: hp.sample(xh_dev0.clone(), noise_dev), 1, 2, dev, flush)
+                modes[prec] = B / (ms * 1e-3)
+                del hp
+            line["precision_lines"] = {"unit": "samples/s", "workload": "the headline batch, device-resident, 2 timed runs per mode",
+                                       args.precision: value, **modes,
+                                       "note": "bf16 / f16 / tf32 keep north_star's letter (16-bit or TF32 operands only in the MLP "
+                                               "contractions); f16fast also runs the edge kernels' first layer in packed f16x2"}
+        except Exception as ex:
+            line["precision_lines"] = {"error": repr(ex)[:300]}
         for bs in [int(v) for v in args.sweep.split(",") if v]:
             try:
                 also.append(side_workload("config3", dev, args.precision, flush, n_samples=bs, full_run=False))

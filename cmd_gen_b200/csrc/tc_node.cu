@@ -298,6 +298,10 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             // busy whatever the tile's node count; chunks past the tile's last node are skipped.
             const float b3c = a.b3[ch];
             wait_acc(0);
+            // xa is re-used for t: the accumulator-full mbarrier (completed by tcgen05.commit after the last MMA that read the
+            // tile) already orders these stores after every warp's staging stores AND the tensor core's reads; the CTA
+            // barrier among the compute warps adds nothing to that but lets racecheck, which does not model the commit, see it
+            named_bar_sync(1, COMPUTE_WARPS * 32);
             if (tr) trace_mark(a.trace, 0, 0, 3);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
 #pragma unroll
             for (int j = 0; j < 16; ++j) r[j] = (16 * cpar + j < n_valid) ? hrow[(size_t)(16 * cpar + j) * H] : 0.f;
             wait_acc(1);
+            named_bar_sync(1, COMPUTE_WARPS * 32);                                   // xb is re-used for the new h: see above
             if (tr) trace_mark(a.trace, 0, 0, 5);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
