@@ -833,3 +833,35 @@ def test_f16_range_is_flagged_and_rerun_in_tf32(capsys):
     hb.plan(g["counts"], g["sizes"])
     hb.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), t)
     assert hb.flags().f16_range & 1
+
+
+def test_sample_pockets_equals_pocket_by_pocket_sampling():
+    """The config-4 driver on one rank: every pocket's result must equal sampling that pocket ALONE with the same seed and
+    global sample ids (the device noise generator makes a sample independent of what it is batched or sharded with), and
+    the handle must walk the ragged list on one grow-only workspace."""
+    from cmd_gen_b200.sharding import sample_pockets
+    from cmd_gen_b200.utils import scatter_mean
+    cfg = DynamicsConfig(n_layers=2)
+    ddpm = build_ddpm(cfg, 0, 500)
+    gen = torch.Generator().manual_seed(8)
+    sizes, n_ph, n_samples = [60, 33, 91], [5, 8, 4], 3
+    pockets = []
+    for n in sizes:
+        p = make_pocket_batch([n], 20, seed=int(torch.randint(0, 1000, (1,), generator=gen)))
+        pockets.append({"x": p["x"], "one_hot": p["one_hot"]})
+    out = sample_pockets(ddpm, pockets, n_samples, n_ph, seed=21, timesteps=8)
+    assert [o.shape for o in out] == [(n_samples * k, 11) for k in n_ph]
+    h = ddpm.dynamics.handle(DEV)
+    assert h.graph_captures() == len(pockets)
+    for i in (2, 0):                                               # any order, any batching: same clouds
+        x = pockets[i]["x"].to(DEV)
+        pk = {"x": x.repeat(n_samples, 1), "one_hot": pockets[i]["one_hot"].to(DEV).repeat(n_samples, 1),
+              "size": torch.full((n_samples,), sizes[i], device=DEV), "mask": torch.repeat_interleave(torch.arange(n_samples, device=DEV), sizes[i])}
+        com_before = scatter_mean(pk["x"], pk["mask"])
+        ddpm.noise_seed, ddpm.sample_ids = 21, torch.arange(i * n_samples, (i + 1) * n_samples)
+        xp, xk, pm, km = ddpm.sample_given_pocket(pk, torch.full((n_samples,), n_ph[i]), timesteps=8)
+        ddpm.noise_seed, ddpm.sample_ids = None, None
+        xp[:, :3] += (com_before - scatter_mean(xk[:, :3], km))[pm]
+        assert torch.equal(xp, out[i])
+        # the clouds sit around their own pocket (original frame), not at the origin
+        assert (xp[:, :3].mean(0) - x.mean(0)).abs().max() < 60.0
