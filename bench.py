@@ -580,8 +580,8 @@ def run_ours(args, rank, world, local_rank):
                 ms = timed_runs(lambda: hp.sample(xh_dev0.clone(), noise_dev), 1, 2, dev, flush)
                 modes[prec] = B / (ms * 1e-3)
                 del hp
-            line["precision_lines"] = {"unit": "samples/s", "workload": "the headline batch, device-resident, 2 timed runs per mode",
-                                       args.precision: value, **modes,
+            line["precision_lines"] = {"unit": "samples/s per GPU", "workload": "the headline batch, device-resident, 2 timed runs per mode (rank 0)",
+                                       args.precision: value / world, **modes,
                                        "note": "bf16 / f16 / tf32 keep north_star's letter (16-bit or TF32 operands only in the MLP "
                                                "contractions); f16fast also runs the edge kernels' first layer in packed f16x2"}
         except Exception as ex:
