@@ -865,3 +865,30 @@ def test_sample_pockets_equals_pocket_by_pocket_sampling():
         assert torch.equal(xp, out[i])
         # the clouds sit around their own pocket (original frame), not at the origin
         assert (xp[:, :3].mean(0) - x.mean(0)).abs().max() < 60.0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16fast"])
+def test_sampler_edge_shapes(prec):
+    """Degenerate layouts through the mirror: one sample, one pharmacophore point, a one-residue pocket, a single
+    denoising step, as many frames as steps, a sample without pharmacophore points, 300 samples in one batch — finite,
+    COM-free, one-hot, and reproducible with the device noise generator."""
+    cfg = DynamicsConfig(n_layers=2)
+    ddpm = build_ddpm(cfg, 0, 500, prec)
+    ddpm.noise_seed = 5
+    cases = [([40], [1], 1, 1), ([1], [3], 4, 4), ([25, 30], [4, 0], 6, 3), ([12] * 300, [2] * 300, 2, 1)]
+    for sizes, counts, steps, frames in cases:
+        runs = []
+        for _ in range(2):
+            pk = _ca_pocket_dict(sizes, seed=70)
+            out = ddpm.sample_given_pocket(pk, torch.tensor(counts), return_frames=frames, timesteps=steps)
+            xp, xk, pm, km = out
+            runs.append(xp.clone())
+            fin = xp if frames == 1 else xp[0]
+            assert torch.isfinite(xp).all() and torch.isfinite(xk).all()
+            assert fin.shape == (sum(counts), 11) and torch.all(fin[:, 3:].sum(1) == 1)
+            if sum(counts):
+                tot = torch.zeros(len(sizes), 3, device=DEV).index_add_(0, pm, fin[:, :3])
+                assert tot.abs().max() <= 5e-2 * max(1.0, float(fin[:, :3].abs().max()))
+            if frames > 1:
+                assert xp.shape[0] == frames and xk.shape[0] == frames
+        assert torch.equal(runs[0], runs[1])
