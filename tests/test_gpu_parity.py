@@ -862,7 +862,10 @@ def test_sample_pockets_equals_pocket_by_pocket_sampling():
         xp, xk, pm, km = ddpm.sample_given_pocket(pk, torch.full((n_samples,), n_ph[i]), timesteps=8)
         ddpm.noise_seed, ddpm.sample_ids = None, None
         xp[:, :3] += (com_before - scatter_mean(xk[:, :3], km))[pm]
-        assert torch.equal(xp, out[i])
+        # the sampler itself is deterministic; the frame shift goes through torch's index_add_ (atomics on CUDA, like the
+        # reference's torch_scatter), whose summation order — hence the last bit of the pocket COM — varies run to run
+        assert torch.equal(xp[:, 3:], out[i][:, 3:])
+        assert (xp[:, :3] - out[i][:, :3]).abs().max() <= 4e-6 * max(1.0, float(xp[:, :3].abs().max()))
         # the clouds sit around their own pocket (original frame), not at the origin
         assert (xp[:, :3].mean(0) - x.mean(0)).abs().max() < 60.0
 
