@@ -222,6 +222,16 @@ __device__ __forceinline__ void ldg4_if(uint4& v, const void* p, bool take)
         "@q ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
         "}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((int)take));
 }
+// the same without initialised destinations: the registers hold garbage when `take` is clear — the caller must only
+// use them under the same predicate (saves the two CS2R per call that zero a uint4)
+__device__ __forceinline__ void ldg4_if_noinit(uint4& v, const void* p, bool take)
+{
+    asm("{\n"
+        ".reg .pred q;\n"
+        "setp.ne.s32 q, %5, 0;\n"
+        "@q ld.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+        "}" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "r"((int)take));
+}
 __device__ __forceinline__ uint4 ldg_u4(const void* p)
 {
     uint4 v;

@@ -59,7 +59,10 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
-constexpr int REGS_MMA = 32;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless;
+#ifndef EDGE_REGS_MMA
+#define EDGE_REGS_MMA 32
+#endif
+constexpr int REGS_MMA = EDGE_REGS_MMA;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless;
                                                   // 40 (no spill) left the producers' setmaxnreg.inc no slack and measured no faster
 #ifndef EDGE_REGS_PACKED_PRODUCER
 #define EDGE_REGS_PACKED_PRODUCER 104
@@ -355,8 +358,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
                 // (a predicated load straight into a copy of `cur` chains every reload behind the previous one's arrival)
                 const bool new_run = next_row != cur_row && !(a.dbg & 2);                 // next edge starts a new row run
+#ifdef EDGE_FRESH_NOINIT
+                uint4 fresh;                                                             // only read when new_run (the selects below)
+                ldg4_if_noinit(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
+#else
                 uint4 fresh = make_uint4(0u, 0u, 0u, 0u);
                 ldg4_if(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
+#endif
                 const uint4 nxt = make_uint4(new_run ? fresh.x : cur.x, new_run ? fresh.y : cur.y, new_run ? fresh.z : cur.z, new_run ? fresh.w : cur.w);
                 if (TRACE && i < 2) {                                                    // timeline only: when Pa / Pb of this edge have landed
                     uint32_t t0, t1;
