@@ -21,7 +21,7 @@ EXPORTS = [
     "dp_set_weights", "dp_set_precision", "dp_plan", "dp_build_edges", "dp_get_graph", "dp_dynamics_forward",
     "dp_ddpm_update", "dp_set_step_table", "dp_sample", "dp_sample_host", "dp_get_flags", "dp_reset_flags",
     "dp_launch_count", "dp_profile_enable", "dp_profile_read", "dp_pointcloud_stats",
-    "dp_sample_ex", "dp_fill_noise", "dp_sample_host_seeded", "dp_graph_captures",
+    "dp_sample_ex", "dp_fill_noise", "dp_sample_host_seeded", "dp_graph_captures", "dp_set_update_pocket_coords",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library():
     lib.dp_weight_count.restype = i64
     lib.dp_set_weights.argtypes = [vp, vp, i64]
     lib.dp_set_precision.argtypes = [vp, C.c_int]
+    lib.dp_set_update_pocket_coords.argtypes = [vp, C.c_int32]
     lib.dp_plan.argtypes = [vp, i32, vp, vp, i64]
     lib.dp_build_edges.argtypes = [vp, vp, vp]
     lib.dp_get_graph.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), vp]
@@ -157,6 +158,10 @@ class Handle:
 
     def set_precision(self, precision: str):
         _check(self.lib.dp_set_precision(self.h, PRECISION_MODES[precision]))
+
+    def set_update_pocket_coords(self, on: bool):
+        """EGNNDynamics(update_pocket_coords=...): joint mode moves (and returns velocities for) the pocket nodes too."""
+        _check(self.lib.dp_set_update_pocket_coords(self.h, 1 if on else 0))
 
     def plan(self, phar_counts, res_counts, edge_capacity: int = 0):
         pc = torch.as_tensor(phar_counts, dtype=torch.int32, device="cpu").contiguous()

@@ -145,6 +145,10 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_SEG")) h->seg_mode = !strcmp(m, "units") ? 1 : !strcmp(m, "lanes") ? 2 : 0;   // tests force a scheme
     if (const char* m = getenv("DIFFPHAR_TMA_FILL")) h->tma_fill = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_NODE_MC")) h->node_mc = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_NODE_SPLIT")) h->node_split = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_TRACE_CTA")) h->trace_cta = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_TRACE_V")) h->trace_v = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
     if (const char* m = getenv("DIFFPHAR_SKIP")) h->skip_mask = atoi(m);
     if (const char* m = getenv("DIFFPHAR_GRAPH")) h->graph_mode = !strcmp(m, "scan") ? 1 : !strcmp(m, "cells") ? 2 : !strcmp(m, "fused") ? 4 : 0;
@@ -366,6 +370,14 @@ extern "C" int dp_set_precision(dp_handle* h, int precision)
     DP_CHECK(h, DP_ERR_INVALID, "null handle");
     DP_CHECK(precision >= DP_FP32 && precision <= DP_F16_FAST32, DP_ERR_INVALID, "unknown precision %d", precision);
     h->precision = precision;
+    return DP_OK;
+}
+
+extern "C" int dp_set_update_pocket_coords(dp_handle* h, int32_t on)
+{
+    DP_CHECK(h, DP_ERR_INVALID, "null handle");
+    if (h->joint != (on != 0)) drop_graph(h);                 // the captured step bakes the coordinate mask
+    h->joint = on != 0;
     return DP_OK;
 }
 
@@ -599,6 +611,10 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         DP_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
     } else if (!(h->skip_mask & 16) && (rc = launch_build_edges(h, p.x_in, st))) return rc;
     float* x_cur = p.x_a; float* x_next = p.x_b;
+    // update_coords_mask (dynamics.py:104-107): the phar rows [0, Np), or every row in joint mode.  The CSR puts the moving
+    // rows' edges first, so the coordinate MLP runs on counts[1] = E_p edges (conditional) or on all counts[0] = E (joint).
+    const int n_moving = h->joint ? p.N : p.Np;
+    const int* n_coord_edges = h->joint ? p.counts : p.counts + 1;
 
     auto project = [&](int v) -> int {
         const ProjSet& ps = W.proj[v];
@@ -630,7 +646,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
         e.p = p.pq; e.ldp = pin.lin.out; e.off_a = pin.off_gcl; e.off_b = pin.off_gcl + H;
         e.wr = L.wr; e.wd = L.wd; e.w2t = L.e2.wt; e.b2 = L.e2.b; e.wv = L.wa; e.bv = L.ba;
         e.x = x_cur; e.d0 = p.d0; e.erow = p.erow; e.ecol = p.col; e.rowptr = p.rowptr;
-        e.edst = p.edst; e.n_moving = p.Np; e.ecap = (int)p.Ecap; e.tma_fill = h->tma_fill; e.dbg = h->dbg; e.contig = p.seg_lanes;
+        e.edst = p.edst; e.n_moving = n_moving; e.ecap = (int)p.Ecap; e.tma_fill = h->tma_fill; e.dbg = h->dbg; e.contig = p.seg_lanes;
         e.n_edges = p.counts; e.agg = p.agg; e.partials = p.partials; e.escal = nullptr;
         e.coord = 0; e.attention = c.attention; e.use_tanh = c.use_tanh; e.trace = h->trace_kernel == 2 ? h->trace : nullptr;
         e.range_flag = p.nan_flag + 2;
@@ -657,14 +673,14 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.p = p.pq; q.ldp = pc.lin.out; q.off_a = pc.off_coord; q.off_b = pc.off_coord + H;
             q.wr = Cw.wr; q.wd = Cw.wd; q.w2t = Cw.c2.wt; q.b2 = Cw.c2.b; q.wv = Cw.w4; q.bv = 0.f;
             q.x = x_cur; q.d0 = p.d0; q.erow = p.erow; q.ecol = p.col; q.rowptr = p.rowptr;
-            q.edst = p.edst; q.n_moving = p.Np; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
-            q.n_edges = p.counts + 1; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
+            q.edst = p.edst; q.n_moving = n_moving; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
+            q.n_edges = n_coord_edges; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr; q.range_flag = p.nan_flag + 2;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
             // (a coordinate-mode kernel with row-owned tiles that finishes its phar rows itself — no second launch — was built,
             //  parity-green, and measured 5 % SLOWER per step; commit 5e2a79c, profiles/r05e_ab_summary.txt)
             prof_begin(h, PROF_EDGE_COORD, st);
-            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, st);
+            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, n_moving, st);
             prof_end(h, st);
             if (rc) return rc;
             float* t = x_cur; x_cur = x_next; x_next = t;
@@ -683,8 +699,10 @@ extern "C" int dp_dynamics_forward(dp_handle* h, const float* xh_phar, const flo
     DP_CHECK(t_dev || !h->cfg.condition_time, DP_ERR_INVALID, "dp_dynamics_forward: t is required");
     DP_CHECK(t_stride == 0 || t_stride == 1, DP_ERR_INVALID, "t_stride must be 0 or 1");
     cudaStream_t st = (cudaStream_t)stream;
+    DP_CHECK(!h->joint || out_res, DP_ERR_INVALID, "dp_dynamics_forward: joint mode returns the pocket velocities, out_res_dev is required");
     if ((rc = run_denoiser(h, xh_phar, xh_res, t_dev ? t_dev : h->plan.t_const, nullptr, 0, t_stride, out_phar, out_res, st))) return rc;
-    return launch_nan_fixup(h, out_phar, out_res, st);
+    if ((rc = launch_nan_fixup(h, out_phar, out_res, st))) return rc;
+    return h->joint ? launch_velocity_center(h, out_phar, out_res, st) : DP_OK;     // dynamics.py:133-136
 }
 
 // --------------------------------------------------------------------------------------
@@ -830,6 +848,7 @@ extern "C" int dp_sample_ex(dp_handle* h, float* pocket, const dp_sample_opts* o
     int rc = require(h, true, true);
     if (rc) return rc;
     DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
+    DP_CHECK(!h->joint, DP_ERR_STATE, "the pocket-conditioned sampler needs update_pocket_coords = False (conditional_model.py:18)");
     DP_CHECK(pocket && o && out_phar, DP_ERR_INVALID, "dp_sample_ex: null argument");
     const int F = o->return_frames > 1 ? o->return_frames : 1;
     DP_CHECK(F <= h->n_steps && h->n_steps % F == 0, DP_ERR_INVALID,
@@ -880,6 +899,7 @@ static int sample_host_common(dp_handle* h, const float* pocket_host, const floa
     int rc = require(h, true, true);
     if (rc) return rc;
     DP_CHECK(pocket_host && out_phar_host, DP_ERR_INVALID, "dp_sample_host: null buffer");
+    DP_CHECK(!h->joint, DP_ERR_STATE, "the pocket-conditioned sampler needs update_pocket_coords = False (conditional_model.py:18)");
     DP_CHECK(h->n_steps > 0 && h->plan.step_rows, DP_ERR_STATE, "dp_set_step_table has not been called");
     Plan& p = h->plan; const dp_config& c = h->cfg;
     const int PW = 3 + c.phar_nf, RW = 3 + c.residue_nf;

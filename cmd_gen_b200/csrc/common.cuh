@@ -54,6 +54,21 @@ inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, 
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// the same for a kernel that runs as thread-block clusters of `cluster` CTAs along x (grid.x a multiple of it)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(bool pdl, int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------------------
 // device-side math shared by kernels
 // ---------------------------------------------------------------------------
@@ -262,9 +277,17 @@ struct dp_handle {
     int device = 0;
     int sm_count = 148;
     int precision = 0;
+    bool joint = false;                // dp_set_update_pocket_coords: every node's coordinates move (update_pocket_coords=True, dynamics.py:104-107, 133-136)
     int dbg = 0;                       // DIFFPHAR_DBG: timing-experiment bits (results may be wrong), 0 in production
     int seg_mode = 0;                  // DIFFPHAR_SEG: 0 automatic, 1 units, 2 lanes (Plan::seg_lanes)
     int node_pair = 0;                 // DIFFPHAR_NODE_PAIR: node kernel as CTA pairs (cluster of 2, tcgen05 cta_group::2)
+    int node_mc = 0;                   // DIFFPHAR_NODE_MC: node kernel in clusters of 2 whose weight panels arrive by TMA multicast (each CTA
+                                       // fetches half of every panel for both).  Measured 3 % SLOWER (profiles/r06a_ab_summary.txt): the GEMM
+                                       // phases are paced by the MMAs' own operand fetch, not by the L2 -> SM weight stream
+    int node_split = 64;               // DIFFPHAR_NODE_SPLIT: nodes per tile for the tiles that hold phar rows (one projection block more
+                                       // than the rest); 0 = uniform tiles
+    int trace_cta = 0;                 // DIFFPHAR_TRACE_CTA: which CTA of the traced kernel writes the timeline
+    int trace_v = -1;                  // DIFFPHAR_TRACE_V: only the node launch of h version v writes it (-1: every launch, the last one stays)
     int tma_fill = 1;                  // DIFFPHAR_TMA_FILL=0: resident weights through LDG + tcgen05.st (A/B; EdgeArgs::tma_fill)
     bool pdl = false;                  // programmatic dependent launch between the kernels of a step (DIFFPHAR_PDL=1 enables; measured neutral inside graph replay)
     int skip_mask = 0;                 // DIFFPHAR_SKIP (timing experiments only, results are garbage): 1 edge msg, 2 node, 4 coord edge, 8 coord finish, 16 graph, 32 encode/decode, 64 ddpm
@@ -355,7 +378,8 @@ int egnn_f32_init();
 // 2: pocket nodes = h_base + t * w_time (their type features are constant during sampling), phar nodes in full
 int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
                         const int* step_idx, int row_stride, int t_stride, int base_mode, cudaStream_t st);
-int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStream_t st);
+int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, int n_moving, cudaStream_t st);
+int launch_velocity_center(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st);
 int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* out_res, cudaStream_t st);
 int launch_nan_fixup(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st);
 struct DdpmArgs {

@@ -440,15 +440,15 @@ int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res,
     return DP_OK;
 }
 
-int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, cudaStream_t st)
+int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, int n_moving, cudaStream_t st)
 {
     const Plan& p = h->plan; const dp_config& c = h->cfg;
-    if (p.Np == 0) return DP_OK;
+    if (n_moving == 0) return DP_OK;
     CoordFinishArgs a;
     a.x_cur = x_cur; a.x_next = x_next; a.escal = p.escal; a.rowptr = p.rowptr; a.col = p.col;
-    a.Np = p.Np; a.norm_constant = c.norm_constant; a.coords_range = c.coords_range;
+    a.Np = n_moving; a.norm_constant = c.norm_constant; a.coords_range = c.coords_range;
     a.norm_factor = c.normalization_factor; a.use_tanh = c.use_tanh; a.mean = c.aggregation_mean;
-    DP_CUDA(launch_kernel(h->pdl, coord_finish_kernel, dim3((p.Np * 8 + 255) / 256), dim3(256), 0, st, a));
+    DP_CUDA(launch_kernel(h->pdl, coord_finish_kernel, dim3((n_moving * 8 + 255) / 256), dim3(256), 0, st, a));
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;
@@ -481,6 +481,43 @@ int launch_nan_fixup(dp_handle* h, float* out_phar, float* out_res, cudaStream_t
     const Plan& p = h->plan; const dp_config& c = h->cfg;
     const int n = p.Np > p.Nr ? p.Np : p.Nr;
     nan_fixup_kernel<<<(n + 255) / 256 + 1, 256, 0, st>>>(out_phar, out_res, p.Np, p.Nr, c.phar_nf, c.residue_nf, p.nan_flag);
+    h->launches += 1;
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+// Joint mode only (update_pocket_coords=True): vel = remove_mean_batch(vel, mask), dynamics.py:133-136 — the mean over ALL
+// nodes of a sample (phar and pocket) leaves the velocity columns.  One CTA per sample; fixed-order tree reduction.
+__global__ void __launch_bounds__(256) velocity_center_kernel(float* out_phar, float* out_res, const int* phar_off, const int* res_off, int P, int R)
+{
+    __shared__ float red[3][256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int p0 = phar_off[b], np = phar_off[b + 1] - p0, r0 = res_off[b], nr = res_off[b + 1] - r0;
+    const int PW = 3 + P, RW = 3 + R, n = np + nr;
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int i = tid; i < n; i += 256) {
+        const float* v = i < np ? out_phar + (size_t)(p0 + i) * PW : out_res + (size_t)(r0 + i - np) * RW;
+        s[0] += v[0]; s[1] += v[1]; s[2] += v[2];
+    }
+    for (int c = 0; c < 3; ++c) red[c][tid] = s[c];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) for (int c = 0; c < 3; ++c) red[c][tid] += red[c][tid + o];
+        __syncthreads();
+    }
+    const float inv = 1.0f / (float)max(n, 1);
+    const float m0 = red[0][0] * inv, m1 = red[1][0] * inv, m2 = red[2][0] * inv;
+    for (int i = tid; i < n; i += 256) {
+        float* v = i < np ? out_phar + (size_t)(p0 + i) * PW : out_res + (size_t)(r0 + i - np) * RW;
+        v[0] -= m0; v[1] -= m1; v[2] -= m2;
+    }
+}
+
+int launch_velocity_center(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st)
+{
+    const Plan& p = h->plan; const dp_config& c = h->cfg;
+    if (p.B == 0) return DP_OK;
+    velocity_center_kernel<<<p.B, 256, 0, st>>>(out_phar, out_res, p.phar_off, p.res_off, c.phar_nf, c.residue_nf);
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;

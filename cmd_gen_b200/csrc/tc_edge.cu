@@ -358,8 +358,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
                 // (a predicated load straight into a copy of `cur` chains every reload behind the previous one's arrival)
                 const bool new_run = next_row != cur_row && !(a.dbg & 2);                 // next edge starts a new row run
-#ifdef EDGE_FRESH_NOINIT
-                uint4 fresh;                                                             // only read when new_run (the selects below)
+#ifndef EDGE_FRESH_INIT
+                // the destination registers are NOT initialised (only read under new_run by the selects below): saves the two
+                // CS2R per edge that zero a uint4 — message launch 27.1 -> 26.6 us at config 2 (profiles/r06b_ab_summary.txt)
+                uint4 fresh;
                 ldg4_if_noinit(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
 #else
                 uint4 fresh = make_uint4(0u, 0u, 0u, 0u);

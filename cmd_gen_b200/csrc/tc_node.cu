@@ -56,6 +56,10 @@ struct NodeArgs {
     const float* bp;                             // projection bias [n_blocks * 256], pre-scaled by 1/2 like the weight image
     __half* pq; int ldp; int n_blocks;           // projection output [N][ldp] f16 (pre-scaled by 1/2), n_blocks x 256 channels
     int stride; int n_mma;                       // nodes per CTA (<= NT) and the UMMA N that covers them (multiple of 16)
+    int tp; int sp;                              // the first `tp` CTAs take `sp` nodes each (sp <= stride): the tiles that hold the moving (phar)
+                                                 // rows run one projection block more than the others (Qa), so they get fewer nodes — the
+                                                 // launch ends with its slowest CTA.  tp = 0: uniform tiles.  Single-CTA kernel only.
+    int trace_cta;                               // which CTA writes the debug timeline
     int row_block; int n_moving;                 // block `row_block` (row part Qa of the coordinate MLP, -1: none) is only read for rows < n_moving
                                                  // (update_coords_mask keeps phar rows, dynamics.py:105-107): tiles past them skip it
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
@@ -67,7 +71,7 @@ struct NodeArgs {
 // debug timeline of CTA 0: role 0 = compute warp 0, 1 = MMA thread, 2 = TMA thread; 16 slots per (role, row)
 __device__ __forceinline__ void trace_mark(long long* trace, int role, int row, int slot)
 {
-    if (trace && blockIdx.x == 0) trace[(role * 64 + row) * 16 + slot] = clock64();
+    if (trace) trace[(role * 64 + row) * 16 + slot] = clock64();
 }
 
 // 8 MMAs of one K panel: D[256 x 128] (+)= Wpanel[256 x 64] * Xpanel[128 x 64]^T
@@ -164,19 +168,31 @@ __device__ __forceinline__ void store_k16(unsigned char* tile, int i, int k, flo
     else *reinterpret_cast<__half*>(p) = __float2half_rn(v);
 }
 
-template <int FMT>
+// MC = the launch runs as clusters of two CTAs that SHARE the weight stream: both walk the same panel sequence on their
+// own node tiles; CTA r fetches half r of every 32 KB panel and the TMA multicast delivers it to the same ring slot of
+// both CTAs (one L2 read instead of two).  Why: all 148 CTAs pull the same 640-896 KB per launch and the L2's output —
+// ~6 300 B/clk for the whole chip, 43 B/clk per SM — is what paces the GEMM phases (a panel lands every ~730 cycles,
+// its 8 MMAs need ~400).  A ring slot is free when BOTH CTAs' MMAs have read it (multicast tcgen05.commit, count 2);
+// a slot is full when both halves have landed (32 KB of complete_tx on the CTA's own mbarrier).
+template <int FMT, bool MC>
 __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const unsigned char* __restrict__ w_img)
 {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // the same offset in every CTA (multicast targets it)
     NodeSmem& s = *reinterpret_cast<NodeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n0 = blockIdx.x * a.stride;
-    const int skip_b = (a.row_block >= 0 && n0 >= a.n_moving) ? a.row_block : -1;   // CTA-uniform: all three roles agree
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    const int cta = (int)blockIdx.x;
+    const int my_stride = cta < a.tp ? a.sp : a.stride;
+    const int n0 = cta < a.tp ? cta * a.sp : a.tp * a.sp + (cta - a.tp) * a.stride;
+    const int n_mma = cta < a.tp ? (a.sp + 15) / 16 * 16 : a.n_mma;
+    const int n0_first = MC ? (int)(blockIdx.x & ~1u) * a.stride : n0;              // first node of the cluster (tp = 0 there)
+    long long* const trace_p = cta == a.trace_cta ? a.trace : nullptr;
+    const int skip_b = (a.row_block >= 0 && n0_first >= a.n_moving) ? a.row_block : -1;   // cluster-uniform: every role of both CTAs agrees
     const int mlp_panels = a.do_mlp ? 12 : 0;
 
     if (tid == 0) {
-        for (int i = 0; i < N_WS; ++i) { mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), 1); }
+        for (int i = 0; i < N_WS; ++i) { mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), MC ? 2 : 1); }
         for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.bar_x[i]), COMPUTE_WARPS);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), COMPUTE_WARPS); }
         fence_barrier_init();
@@ -184,6 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
     if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), 512);          // 2 x 192 accumulator columns; allocations are powers of two
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();                                              // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_holder;
     pdl_launch_dependents();
@@ -198,12 +215,17 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             for (int g = 0; g < mlp_panels + 4 * a.n_blocks; ++g) {                    // g = panel of the image
                 if (g >= mlp_panels && (g - mlp_panels) / 4 == skip_b) continue;
                 const int slot = p % N_WS;
-                if (lane == 0) trace_mark(a.trace, 2, p, 0);
+                if (lane == 0) trace_mark(trace_p, 2, p, 0);
                 mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS) & 1) ^ 1);
-                if (lane == 0) trace_mark(a.trace, 2, p, 1);
+                if (lane == 0) trace_mark(trace_p, 2, p, 1);
                 if (elect_one()) {
                     mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_PANEL_BYTES);
-                    bulk_g2s(w0 + slot * W_PANEL_BYTES, w_img + (size_t)g * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
+                    if (MC)                                                            // my half, into both CTAs' slot; the peer sends the other half
+                        bulk_g2s_multicast(w0 + slot * W_PANEL_BYTES + rank * (W_PANEL_BYTES / 2),
+                                           w_img + (size_t)g * W_PANEL_BYTES + rank * (W_PANEL_BYTES / 2), W_PANEL_BYTES / 2,
+                                           smem_u32(&s.bar_wfull[slot]), 3);
+                    else
+                        bulk_g2s(w0 + slot * W_PANEL_BYTES, w_img + (size_t)g * W_PANEL_BYTES, W_PANEL_BYTES, smem_u32(&s.bar_wfull[slot]));
                 }
                 __syncwarp();
                 ++p;
@@ -213,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         // ================================ MMA issuer ================================
         // the whole warp runs the control flow (uniform: descriptors stay in uniform registers), one elected lane issues
         {
-            const uint32_t idesc = make_idesc(FMT, 128, a.n_mma);
+            const uint32_t idesc = make_idesc(FMT, 128, n_mma);
             const uint32_t td = warp_uniform(tmem_base);
             const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
             const uint32_t xa = warp_uniform(smem_u32(s.xa)), xb = warp_uniform(smem_u32(s.xb));
@@ -227,18 +249,19 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 for (int kp = 0; kp < k_panels; ++kp, ++p) {
                     const int slot = p % N_WS;
                     if (kp == 4) mbar_wait(smem_u32(&s.bar_x[0]), 0);
-                    if (tr) trace_mark(a.trace, 1, p, 0);
+                    if (tr) trace_mark(trace_p, 1, p, 0);
                     mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS) & 1);
-                    if (tr) trace_mark(a.trace, 1, p, 1);
+                    if (tr) trace_mark(trace_p, 1, p, 1);
                     tc_fence_after();
                     const uint32_t xp = (kp < 4 ? x0 + kp * NX_PANEL : x1 + (kp - 4) * NX_PANEL);
                     if (elect_one()) {
                         issue_panel(td + acc * ACC_COLS, w0 + slot * W_PANEL_BYTES, xp, idesc, kp == 0);
-                        umma_commit(smem_u32(&s.bar_wempty[slot]));
+                        if (MC) umma_commit_multicast(smem_u32(&s.bar_wempty[slot]), 3);
+                        else umma_commit(smem_u32(&s.bar_wempty[slot]));
                         if (kp == k_panels - 1) umma_commit(smem_u32(&s.bar_accfull[acc]));
                     }
                     __syncwarp();
-                    if (tr) trace_mark(a.trace, 1, p, 2);
+                    if (tr) trace_mark(trace_p, 1, p, 2);
                 }
                 acc_uses[acc] += 1;
             };
@@ -280,8 +303,8 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         };
         const bool tr = wid == 0 && lane == 0;
         pdl_wait();
-        if (tr) trace_mark(a.trace, 0, 0, 0);
-        const int n_valid = min(a.stride, a.n_rows - n0);                            // rows of this tile that exist
+        if (tr) trace_mark(trace_p, 0, 0, 0);
+        const int n_valid = min(my_stride, a.n_rows - n0);                           // rows of this tile that exist
         if (a.do_mlp) {
             int rp = 0;                                                              // CSR bounds of the warp's rows: issued first
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
@@ -289,10 +312,10 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             if (lane < ROWS_PER_WARP && n0 + ROWS_PER_WARP * wid + lane < a.n_rows) code = a.aggv.src[n0 + ROWS_PER_WARP * wid + lane];
             stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
             publish(3);
-            if (tr) trace_mark(a.trace, 0, 0, 1);
+            if (tr) trace_mark(trace_p, 0, 0, 1);
             stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp, code);
             publish(0);
-            if (tr) trace_mark(a.trace, 0, 0, 2);
+            if (tr) trace_mark(trace_p, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> xa (the n0 MMAs have all retired: acc_full follows them)
             // A warp takes every other 16-column chunk (i0 = 16 (2 cc + cpar)), so both warps of a channel half stay
             // busy whatever the tile's node count; chunks past the tile's last node are skipped.
@@ -302,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             // tile) already orders these stores after every warp's staging stores AND the tensor core's reads; the CTA
             // barrier among the compute warps adds nothing to that but lets racecheck, which does not model the commit, see it
             named_bar_sync(1, COMPUTE_WARPS * 32);
-            if (tr) trace_mark(a.trace, 0, 0, 3);
+            if (tr) trace_mark(trace_p, 0, 0, 3);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
                 const int i0 = 16 * (2 * cc + cpar);
@@ -323,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             }
             release_acc(0);
             publish(1);
-            if (tr) trace_mark(a.trace, 0, 0, 4);
+            if (tr) trace_mark(trace_p, 0, 0, 4);
             // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> xb
             const float b4c = a.b4[ch];
             float* hrow = a.h + (size_t)n0 * H + ch;
@@ -332,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             for (int j = 0; j < 16; ++j) r[j] = (16 * cpar + j < n_valid) ? hrow[(size_t)(16 * cpar + j) * H] : 0.f;
             wait_acc(1);
             named_bar_sync(1, COMPUTE_WARPS * 32);                                   // xb is re-used for the new h: see above
-            if (tr) trace_mark(a.trace, 0, 0, 5);
+            if (tr) trace_mark(trace_p, 0, 0, 5);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
                 const int i0 = 16 * (2 * cc + cpar);
@@ -354,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             }
             release_acc(1);
             publish(2);
-            if (tr) trace_mark(a.trace, 0, 0, 6);
+            if (tr) trace_mark(trace_p, 0, 0, 6);
         } else {
             stage_h<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane);
             publish(2);
@@ -368,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             const float bias = a.bp[b * 256 + ch];
             __half* dst = a.pq + (size_t)n0 * a.ldp + (size_t)b * 256 + ch;
             wait_acc(acc);
-            if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
+            if (tr && b < 4) trace_mark(trace_p, 0, 0, 7 + 2 * b);
 #pragma unroll 1
             for (int cc = 0; cc < 3; ++cc) {
                 const int i0 = 16 * (2 * cc + cpar);
@@ -381,12 +404,13 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                     if (i0 + j < n_valid) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
             }
             release_acc(acc);
-            if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
+            if (tr && b < 4) trace_mark(trace_p, 0, 0, 8 + 2 * b);
         }
         if (big > 32000.f) atomicOr(a.range_flag, 1);                                // pq is f16 (pre-halved): Pa' + Pb' must stay finite
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();                                              // nobody leaves while the peer's commits / copies may still target it
     if (wid == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
@@ -454,6 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
     const int skip_b = (a.row_block >= 0 && n0_pair >= a.n_moving) ? a.row_block : -1;   // pair-uniform
     const int mlp_panels = a.do_mlp ? 12 : 0;
     const int nm = a.n_mma;                                                  // B rows per CTA (multiple of 16); the MMA's N = 2 nm
+    long long* const trace_p = blockIdx.x == 0 ? a.trace : nullptr;
     const uint32_t ship_bytes = (uint32_t)(NX_PANEL + nm * 128);             // panel 0 whole + rows < nm of panel 1 (rows >= nm are never read)
 
     if (tid == 0) {
@@ -483,9 +508,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
         for (int g = 0; g < mlp_panels + 4 * a.n_blocks; ++g) {
             if (g >= mlp_panels && (g - mlp_panels) / 4 == skip_b) continue;
             const int slot = p % N_WS2;
-            if (lane == 0) trace_mark(a.trace, 2, p, 0);
+            if (lane == 0) trace_mark(trace_p, 2, p, 0);
             mbar_wait(smem_u32(&s.bar_wempty[slot]), ((p / N_WS2) & 1) ^ 1);
-            if (lane == 0) trace_mark(a.trace, 2, p, 1);
+            if (lane == 0) trace_mark(trace_p, 2, p, 1);
             if (elect_one()) {
                 mbar_expect_tx(smem_u32(&s.bar_wfull[slot]), W_HALF_BYTES);
                 bulk_g2s(w0 + slot * W_HALF_BYTES, w_img + (size_t)g * W_PANEL_BYTES + (size_t)rank * W_HALF_BYTES, W_HALF_BYTES,
@@ -516,11 +541,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
                 for (int kp = 0; kp < k_panels; ++kp, ++p) {
                     const int slot = p % N_WS2;
                     if (kp == 4) wait_tile(0, -1);
-                    if (lane == 0) trace_mark(a.trace, 1, p, 0);
+                    if (lane == 0) trace_mark(trace_p, 1, p, 0);
                     mbar_wait(smem_u32(&s.bar_wfull[slot]), (p / N_WS2) & 1);
                     mbar_wait(smem_u32(&s.bar_wpeer[slot]), (p / N_WS2) & 1);      // the peer's half arrived through ITS async proxy
                     tc_fence_after();
-                    if (lane == 0) trace_mark(a.trace, 1, p, 1);
+                    if (lane == 0) trace_mark(trace_p, 1, p, 1);
                     const uint32_t xp = (kp < 4 ? x0 + kp * NX_PANEL : x1 + (kp - 4) * NX_PANEL);
                     if (elect_one()) {
                         issue_panel_pair(td + acc * ACC_COLS, w0 + slot * W_HALF_BYTES, xp, idesc, kp == 0);
@@ -528,7 +553,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
                         if (kp == k_panels - 1) umma_commit_pair(smem_u32(&s.bar_accfull[acc]), 3);
                     }
                     __syncwarp();
-                    if (lane == 0) trace_mark(a.trace, 1, p, 2);
+                    if (lane == 0) trace_mark(trace_p, 1, p, 2);
                 }
                 acc_uses[acc] += 1;
             };
@@ -612,7 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
         };
         const bool tr = wid == 0 && lane == 0;
         pdl_wait();
-        if (tr) trace_mark(a.trace, 0, 0, 0);
+        if (tr) trace_mark(trace_p, 0, 0, 0);
         if (a.do_mlp) {
             int rp = 0;
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
@@ -620,14 +645,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
             if (lane < ROWS_PER_WARP && n0 + ROWS_PER_WARP * wid + lane < a.n_rows) code = a.aggv.src[n0 + ROWS_PER_WARP * wid + lane];
             stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
             publish(3, -1, nullptr);
-            if (tr) trace_mark(a.trace, 0, 0, 1);
+            if (tr) trace_mark(trace_p, 0, 0, 1);
             stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp, code);
             publish(0, -1, nullptr);
-            if (tr) trace_mark(a.trace, 0, 0, 2);
+            if (tr) trace_mark(trace_p, 0, 0, 2);
             // ---- epilogue 1: t = SiLU(D1 + b3) -> K panels 2 rank, 2 rank + 1 of both xa tiles
             const float b3c = a.b3[ch];
             wait_acc(0);
-            if (tr) trace_mark(a.trace, 0, 0, 3);
+            if (tr) trace_mark(trace_p, 0, 0, 3);
 #pragma unroll 1
             for (int c = g; c < n_chunks; c += 4) {
                 const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
@@ -648,12 +673,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
             }
             release_acc(0);
             publish(1, 0, s.xa);
-            if (tr) trace_mark(a.trace, 0, 0, 4);
+            if (tr) trace_mark(trace_p, 0, 0, 4);
             // ---- epilogue 2: h <- h + D2 + b4 (fp32, in place) and its 16-bit copy -> both xb tiles.  The staging
             // buffer is free again: acc 1 is full only after GEMM 2 consumed the t tiles, i.e. after the t shipment landed.
             const float b4c = a.b4[ch];
             wait_acc(1);
-            if (tr) trace_mark(a.trace, 0, 0, 5);
+            if (tr) trace_mark(trace_p, 0, 0, 5);
 #pragma unroll 1
             for (int c = g; c < n_chunks; c += 4) {
                 const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
@@ -673,7 +698,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
             }
             release_acc(1);
             publish(2, 1, s.xb);
-            if (tr) trace_mark(a.trace, 0, 0, 6);
+            if (tr) trace_mark(trace_p, 0, 0, 6);
         } else {
             stage_h<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane);
             publish(2, -1, nullptr);
@@ -686,7 +711,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
             ++cnt;
             const float bias = a.bp[b * 256 + ch];
             wait_acc(acc);
-            if (tr && b < 4) trace_mark(a.trace, 0, 0, 7 + 2 * b);
+            if (tr && b < 4) trace_mark(trace_p, 0, 0, 7 + 2 * b);
 #pragma unroll 1
             for (int c = g; c < n_chunks; c += 4) {
                 const int i0 = 16 * c, owner = i0 >= nm ? 1 : 0, l0 = i0 - owner * nm;
@@ -700,7 +725,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
                     if (l0 + j < nvo) { const float o = v[j] + bias; big = fmaxf(big, fabsf(o)); *d = __float2half_rn(o); }
             }
             release_acc(acc);
-            if (tr && b < 4) trace_mark(a.trace, 0, 0, 8 + 2 * b);
+            if (tr && b < 4) trace_mark(trace_p, 0, 0, 8 + 2 * b);
         }
         if (big > 32000.f) atomicOr(a.range_flag, 1);
     }
@@ -715,8 +740,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) node_pai
 int tc_node_init()
 {
     static_assert(sizeof(NodeSmem) + 1024 <= 232448, "node kernel shared memory exceeds 227 KB");
-    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
-    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
+    DP_CUDA(cudaFuncSetAttribute(node_tc_kernel<tc::FMT_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem) + 1024));
     static_assert(sizeof(NodeSmem2) + 1024 <= 232448, "pair node kernel shared memory exceeds 227 KB");
     DP_CUDA(cudaFuncSetAttribute(node_pair_kernel<tc::FMT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem2) + 1024));
     DP_CUDA(cudaFuncSetAttribute(node_pair_kernel<tc::FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NodeSmem2) + 1024));
@@ -737,8 +764,8 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     a.h = p.h; a.aggv = av; a.n_rows = p.N; a.do_mlp = v > 0;
     if (v > 0) { a.b3 = W.gcl[v - 1].n0.b; a.b4 = W.gcl[v - 1].n2.b; }
     a.bp = ps.b_half; a.pq = reinterpret_cast<__half*>(p.pq); a.ldp = ps.lin.out; a.n_blocks = ps.lin.out / 256;
-    a.row_block = ps.off_coord >= 0 ? ps.off_coord / 256 : -1; a.n_moving = p.Np;
-    a.trace = (h->trace && h->trace_kernel == 1) ? h->trace : nullptr;
+    a.row_block = ps.off_coord >= 0 ? ps.off_coord / 256 : -1; a.n_moving = h->joint ? p.N : p.Np;
+    a.trace = (h->trace && h->trace_kernel == 1 && (h->trace_v < 0 || h->trace_v == v)) ? h->trace : nullptr;
     a.dbg = h->dbg;
     a.fast_silu = (h->precision == DP_F16_FAST || h->precision == DP_F16_FAST32) ? 1 : 0;
     a.range_flag = p.nan_flag + 2;
@@ -749,7 +776,17 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     int stride = (p.N + waves * h->sm_count - 1) / (waves * h->sm_count);
     if (stride < 16) stride = 16;
     a.stride = stride; a.n_mma = (stride + 15) / 16 * 16;
-    const int grid = (p.N + stride - 1) / stride;
+    int grid = (p.N + stride - 1) / stride;
+    a.tp = 0; a.sp = stride; a.trace_cta = h->trace_cta;
+    if (h->node_split && !h->joint && !h->node_pair && !h->node_mc && a.row_block >= 0 && p.Np > 0 && p.Np < p.N) {
+        // tiles with moving rows: h->node_split nodes each; the rest of the SM waves share the remaining nodes evenly
+        const int sp = std::min(stride, h->node_split), tp = (p.Np + sp - 1) / sp, rest = p.N - tp * sp;
+        const int ctas = waves * h->sm_count - tp;
+        if (rest > 0 && ctas > 0) {
+            const int sr = std::max(16, (rest + ctas - 1) / ctas);
+            if (sr <= NT) { a.tp = tp; a.sp = sp; a.stride = sr; a.n_mma = (sr + 15) / 16 * 16; grid = tp + (rest + sr - 1) / sr; }
+        }
+    }
     const unsigned char* img = h->tc->node[v].img[fmt];
     if (h->node_pair) {
         // cluster of two CTAs per pair of tiles (cta_group::2): an odd tile count gets one empty tile
@@ -761,8 +798,17 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
         return DP_OK;
     }
     const int smem = (int)sizeof(NodeSmem) + 1024;
-    if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_BF16>, dim3(grid), dim3(THREADS), smem, st, a, img));
-    else DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_F16>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    if (h->node_mc && grid > 1) {
+        // clusters of two CTAs sharing one multicast weight stream; an odd tile count gets one empty tile
+        const int grid2 = (grid + 1) & ~1;
+        if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel_cluster(h->pdl, 2, node_tc_kernel<tc::FMT_BF16, true>, dim3(grid2), dim3(THREADS), smem, st, a, img));
+        else DP_CUDA(launch_kernel_cluster(h->pdl, 2, node_tc_kernel<tc::FMT_F16, true>, dim3(grid2), dim3(THREADS), smem, st, a, img));
+        h->launches += 1;
+        DP_CUDA(cudaGetLastError());
+        return DP_OK;
+    }
+    if (fmt == tc::FMT_BF16) DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_BF16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
+    else DP_CUDA(launch_kernel(h->pdl, node_tc_kernel<tc::FMT_F16, false>, dim3(grid), dim3(THREADS), smem, st, a, img));
     h->launches += 1;
     DP_CUDA(cudaGetLastError());
     return DP_OK;

@@ -110,6 +110,7 @@ class EGNNDynamics(nn.Module):
             raise _lib.DiffPharError("EGNNDynamics runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self._handle is None or self._handle.device != device:
             self._handle = _lib.Handle(self.cfg, device, self.precision)
+            self._handle.set_update_pocket_coords(bool(self.update_pocket_coords))     # dynamics.py:104-107, 133-136
             self._weights_tag = None
         tag = self._weights_version()
         if tag != self._weights_tag:
@@ -139,8 +140,6 @@ class EGNNDynamics(nn.Module):
             xh_phars = xh_atoms
         if mask_phars is None:
             mask_phars = mask_atoms
-        if self.update_pocket_coords:
-            raise NotImplementedError("joint mode (update_pocket_coords=True) is outside the accelerated path")
         t = torch.as_tensor(t, device=xh_phars.device)
         n_samples = int(t.numel()) if t.numel() > 1 else \
             int(max(int(mask_phars.max()) if mask_phars.numel() else 0,

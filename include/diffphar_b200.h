@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 2
+#define DP_ABI_VERSION 3
 
 typedef enum dp_status {
     DP_OK = 0,
@@ -96,6 +96,12 @@ int dp_destroy(dp_handle* h);
 int64_t dp_weight_count(const dp_handle* h);
 int dp_set_weights(dp_handle* h, const float* blob_host, int64_t n_floats);
 int dp_set_precision(dp_handle* h, int precision);
+/* EGNNDynamics(update_pocket_coords=...) (dynamics.py:16, 104-107, 133-136).  0 (default): pocket-conditioning mode — only
+ * the phar rows' coordinates are updated (update_coords_mask) and the pocket velocities are exactly zero.  1: the joint
+ * mode — every node moves, dp_dynamics_forward returns the pocket velocities too (out_res_dev is then required) and
+ * removes the per-sample mean over ALL nodes from the velocity (remove_mean_batch).  The sampler entry points
+ * (dp_sample*) are ConditionalDDPM's and refuse a handle in joint mode, as the reference asserts (conditional_model.py:18). */
+int dp_set_update_pocket_coords(dp_handle* h, int32_t on);
 
 /* Batch layout.  Sample b owns phar_counts[b] pharmacophore nodes and res_counts[b]
  * pocket nodes; node index space is the reference's: all phar nodes (samples in

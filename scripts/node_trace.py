@@ -1,10 +1,13 @@
 """GPU debug tool: clock64 timeline of CTA 0 of the fused tcgen05 node kernel (last launch of one denoiser
-evaluation at config-2 size).  python scripts/node_trace.py [precision]"""
+evaluation at config-2 size).  python scripts/node_trace.py [precision] [cta] [h version]
+(cta: which CTA writes the timeline, default 0 = a tile with phar rows; h version: which of the 6 node launches, default 3)"""
 import ctypes as C
 import os
 import sys
 
 os.environ["DIFFPHAR_TRACE"] = "1"
+os.environ["DIFFPHAR_TRACE_CTA"] = sys.argv[2] if len(sys.argv) > 2 else "0"
+os.environ["DIFFPHAR_TRACE_V"] = sys.argv[3] if len(sys.argv) > 3 else "3"
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cmd_gen_b200 import _lib

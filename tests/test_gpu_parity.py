@@ -27,13 +27,15 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None):
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, node_mc=None, node_split=None):
     """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "fused" = the scan
     as one launch with a look-back prefix);
     seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
-    node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel."""
+    node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel;
+    node_mc="1": node kernel in clusters of two sharing one multicast weight stream; node_split="0": uniform node tiles."""
     import os
-    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill}
+    forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill,
+              "DIFFPHAR_NODE_MC": node_mc, "DIFFPHAR_NODE_SPLIT": node_split}
     old = {k: os.environ.pop(k, None) for k in forced}
     for k, v in forced.items():
         if v:
@@ -187,6 +189,93 @@ def test_dynamics_tensor_core_modes_vs_reference(name, prec):
     assert h.flags().nan_resets == 0
 
 
+# ----------------------------------------------------------------------------- joint mode
+JOINT_TOL = {"fp32": (2e-5, 0.0), "tf32": (1e-4, 0.02), "f16": (1e-4, 0.02), "f16fast": (2e-4, 0.03), "bf16": (1e-3, 0.05)}
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16", "f16fast", "bf16"])
+@pytest.mark.parametrize("name", ["ca_small", "fa_small", "mean_agg"])
+def test_joint_mode_dynamics_vs_reference(name, prec):
+    """EGNNDynamics(update_pocket_coords=True) (dynamics.py:104-107, 133-136) against the unmodified reference's fp64
+    outputs: the coordinate MLP runs on ALL edges, every row is finished, the pocket velocities come back and the
+    per-sample mean over all nodes is removed."""
+    g = load(f"dynamics_joint_{name}.npz")
+    cfg = case_config(name)
+    h = make_handle(cfg, int(g["wseed"]), prec)
+    h.set_update_pocket_coords(True)
+    h.plan(g["counts"], g["sizes"])
+    B = len(g["sizes"])
+    xs = max(1.0, float(np.abs(g["z"][:, :3]).max()), float(np.abs(g["xh_pocket"][:, :3]).max()))
+    tol_h, tol_v = JOINT_TOL[prec]
+    for i, tv in enumerate(g["t_values"]):
+        out_p, out_r = h.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), torch.full((B,), float(tv)))
+        out_p, out_r = out_p.cpu().numpy(), out_r.cpu().numpy()
+        rp, rr = g[f"eps_phar_f64_{i}"], g[f"eps_res_f64_{i}"]
+        vmax = max(np.abs(rp[:, :3]).max(), np.abs(rr[:, :3]).max())
+        for o, r in ((out_p, rp), (out_r, rr)):
+            assert np.abs(o[:, 3:] - r[:, 3:]).max() <= tol_h * max(1.0, np.abs(r[:, 3:]).max())
+            assert np.abs(o[:, :3] - r[:, :3]).max() <= 1e-5 * xs + tol_v * vmax
+        assert np.abs(out_r[:, :3]).max() > 0.2 * np.abs(rr[:, :3]).max()           # the pocket moves
+    assert h.flags().nan_resets == 0
+    # back to pocket conditioning on the same handle: the pocket stands still again
+    h.set_update_pocket_coords(False)
+    _, out_r = h.dynamics_forward(T(g["z"]), T(g["xh_pocket"]), torch.full((B,), 0.5))
+    assert np.all(out_r.cpu().numpy()[:, :3] == 0.0)
+
+
+def test_joint_mode_mirror_and_sampler_guard():
+    """The mirror's EGNNDynamics(update_pocket_coords=True).forward runs the joint mode; ConditionalDDPM refuses such a
+    dynamics like the reference (conditional_model.py:18) and the C-ABI sampler refuses a handle in joint mode."""
+    from cmd_gen_b200.equivariant_diffusion.dynamics import EGNNDynamics
+    g = load("dynamics_joint_ca_small.npz")
+    cfg = case_config("ca_small")
+    dyn = EGNNDynamics(phar_nf=cfg.phar_nf, residue_nf=cfg.residue_nf, n_dims=3, joint_nf=cfg.joint_nf, hidden_nf=256,
+                       device=DEV, n_layers=cfg.n_layers, attention=True, tanh=True, norm_constant=cfg.norm_constant,
+                       inv_sublayers=cfg.inv_sublayers, normalization_factor=cfg.normalization_factor,
+                       aggregation_method=cfg.aggregation_method, update_pocket_coords=True, edge_cutoff=cfg.edge_cutoff)
+    dyn.load_state_dict(init_weights(cfg, int(g["wseed"])))
+    B = len(g["sizes"])
+    t = torch.full((B, 1), 0.5, device=DEV)
+    out_p, out_r = dyn(T(g["z"]).to(DEV), T(g["xh_pocket"]).to(DEV), t, T(g["mask_phar"]).to(DEV), T(g["mask_res"]).to(DEV))
+    xs = max(1.0, float(np.abs(g["z"][:, :3]).max()), float(np.abs(g["xh_pocket"][:, :3]).max()))
+    assert np.abs(out_r.cpu().numpy()[:, :3] - g["eps_res_f64_1"][:, :3]).max() <= 1e-5 * xs
+    assert np.abs(out_p.cpu().numpy()[:, 3:] - g["eps_phar_f64_1"][:, 3:]).max() <= 2e-5
+    h = dyn.handle(DEV)
+    tab = step_table(gamma_table("polynomial_2", 20, 1e-5), 20)
+    h.set_step_table(tab.rows, tab.final)
+    n_p = int(g["counts"].sum())
+    with pytest.raises(_lib.DiffPharError):
+        h.sample(T(g["xh_pocket"]).to(DEV), torch.zeros(22, n_p, 11, device=DEV))
+
+
+def test_joint_mode_at_full_size_vs_oracle():
+    """config-2 size (all 148 node tiles project the row part, the coordinate MLP covers all ~60 k edges)."""
+    cfg = DynamicsConfig()
+    B, n_res, n_ph = 64, 150, 8
+    pocket = make_pocket_batch([n_res], 20, seed=3, replicate=B)
+    gen = torch.Generator().manual_seed(4)
+    com = pocket["x"][:n_res].mean(0)
+    z = torch.cat([com + 5.0 * torch.randn(B * n_ph, 3, generator=gen), torch.randn(B * n_ph, 8, generator=gen)], 1)
+    xr = torch.cat([pocket["x"], pocket["one_hot"].float() / 4], 1)
+    t = torch.full((B,), 0.4)
+    mp = torch.repeat_interleave(torch.arange(B), n_ph)
+    W = {k: v.double() for k, v in init_weights(cfg, 0).items()}
+    ra, rb, _ = orc.dynamics_forward(W, cfg, z.double(), xr.double(), t.reshape(-1, 1), mp, pocket["mask"], update_pocket_coords=True)
+    ra, rb = ra.numpy(), rb.numpy()
+    xs = float(xr[:, :3].abs().max())
+    for prec, (tol_h, tol_v) in JOINT_TOL.items():
+        if prec == "tf32":
+            continue
+        h = make_handle(cfg, 0, prec)
+        h.set_update_pocket_coords(True)
+        h.plan([n_ph] * B, [n_res] * B)
+        out_p, out_r = h.dynamics_forward(z, xr, t)
+        vmax = max(np.abs(ra[:, :3]).max(), np.abs(rb[:, :3]).max())
+        for o, r in ((out_p.cpu().numpy(), ra), (out_r.cpu().numpy(), rb)):
+            assert np.abs(o[:, 3:] - r[:, 3:]).max() <= tol_h * max(1.0, np.abs(r[:, 3:]).max()), prec
+            assert np.abs(o[:, :3] - r[:, :3]).max() <= 1e-5 * xs + tol_v * vmax, prec
+
+
 def test_tensor_core_modes_at_full_size_agree_with_fp32():
     """config-2 size: every 64-edge tile / 32-edge unit boundary case gets exercised."""
     cfg = DynamicsConfig()
@@ -288,7 +377,8 @@ def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg)
         assert torch.equal(a2.cpu(), a) and torch.equal(r2.cpu(), r)
 
 
-@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"}])
+@pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"},
+                                    {"node_mc": "1"}, {"node_split": "0"}, {"node_split": "32"}, {"node_mc": "1", "seg": "lanes"}])
 def test_alternative_kernel_paths_match_the_default(switch):
     """The switchable kernel variants kept for A/B runs (CTA-pair node kernel with tcgen05 cta_group::2 and DSMEM bulk
     exchange; LDG + tcgen05.st weight fill of the edge kernel) against the default path on a ragged batch: same

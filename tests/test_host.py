@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dp_abi_version() == 2
+    assert lib.dp_abi_version() == 3
 
 
 def test_no_gpu_means_loud_failure(lib):

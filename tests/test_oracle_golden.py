@@ -82,6 +82,33 @@ def test_dynamics_matches_reference(name, dt):
         assert np.abs(a.numpy() - g["eps_phar_f32_scalar_t"]).max() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["ca_small", "fa_small", "mean_agg"])
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+def test_joint_mode_dynamics_matches_reference(name, dt):
+    """update_pocket_coords=True (dynamics.py:104-107, 133-136): every node moves, pocket velocities are returned and the
+    per-sample mean over all nodes is removed; fixtures from the unmodified reference (oracle/make_golden_joint.py)."""
+    g = load(f"dynamics_joint_{name}.npz")
+    cfg = case_config(name)
+    tdt = torch.float32 if dt == "f32" else torch.float64
+    W = {k: v.to(torch.float32).to(tdt) for k, v in init_weights(cfg, int(g["wseed"]), dtype=torch.float64).items()}
+    B = len(g["sizes"])
+    xs = max(1.0, float(np.abs(g["z"][:, :3]).max()), float(np.abs(g["xh_pocket"][:, :3]).max()))
+    tol = 2e-6 if dt == "f32" else 1e-12
+    for i, tv in enumerate(g["t_values"]):
+        t = torch.full((B, 1), float(tv), dtype=torch.float32)
+        a, b, _ = orc.dynamics_forward(W, cfg, T(g["z"]), T(g["xh_pocket"]), t, T(g["mask_phar"]), T(g["mask_res"]),
+                                       update_pocket_coords=True)
+        ra, rb = g[f"eps_phar_{dt}_{i}"], g[f"eps_res_{dt}_{i}"]
+        assert np.abs(rb[:, :3]).max() > 0                              # the pocket really moves in this mode
+        for o, r in ((a.numpy(), ra), (b.numpy(), rb)):
+            assert np.abs(o[:, :3] - r[:, :3]).max() <= tol * xs * 4
+            assert np.abs(o[:, 3:] - r[:, 3:]).max() <= tol * max(1.0, np.abs(r[:, 3:]).max()) * 4
+        # the velocity is mean-free per sample over ALL its nodes
+        vel = torch.cat([a[:, :3], b[:, :3]]).double()
+        m = torch.cat([T(g["mask_phar"]), T(g["mask_res"])])
+        assert float(orc._scatter_mean(vel, m, B).abs().max()) <= 1e-6 * xs
+
+
 @pytest.mark.parametrize("fixture,name", [("sampler_ca_small_T500_n12.npz", "ca_small"),
                                           ("sampler_ca_small_T20.npz", "ca_small"),
                                           ("sampler_fa_small_T500_n6.npz", "fa_small")])
