@@ -147,6 +147,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_NODE_PAIR")) h->node_pair = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_MC")) h->node_mc = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_SPLIT")) h->node_split = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_NODE_H16")) h->node_h16 = atoi(m);
     if (const char* m = getenv("DIFFPHAR_TRACE_CTA")) h->trace_cta = atoi(m);
     if (const char* m = getenv("DIFFPHAR_TRACE_V")) h->trace_v = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
@@ -467,6 +468,12 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.h, (size_t)p.N * H); cv.take(&p.tbuf, (size_t)p.N * H); cv.take(&p.h_base, (size_t)p.Nr * H);
     cv.take(&p.agg, ((size_t)p.N + units * 2) * H);        // [agg rows | partial rows] contiguous (graph.cu edge_dst)
     cv.take(&p.pq, (size_t)p.N * 4 * H);
+    {
+        NodeTiling nt, nu;                                   // with and without the phar-row split (joint mode / switches may change later)
+        node_tiling(h, p.N, p.Np, &nt);
+        node_tiling(h, p.N, 0, &nu);
+        cv.take(&p.h16, (size_t)(std::max(nt.grid, nu.grid) + 1) * node_tile_image_bytes());
+    }
     cv.take(&p.x_in, (size_t)p.N * 3); cv.take(&p.x_a, (size_t)p.N * 3); cv.take(&p.x_b, (size_t)p.N * 3);
     cv.take(&p.z, (size_t)p.Np * PW); cv.take(&p.eps_hat, (size_t)p.Np * PW); cv.take(&p.pocket, (size_t)p.Nr * RW);
     cv.take(&p.out_buf, (size_t)p.Np * PW);

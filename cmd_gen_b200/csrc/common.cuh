@@ -242,6 +242,8 @@ struct Plan {
     float* agg = nullptr;        // [N][H]
     float* partials = nullptr;   // [max(FFMA units, lanes)][2][H]
     float* pq = nullptr;         // [N][1024] fp32 (FFMA mode) or [N][1024] f16 pre-scaled by 1/2 (tcgen05 modes)
+    unsigned char* h16 = nullptr; // 16-bit copy of h as the node kernel's own swizzled B-tile images, one per node tile (tc_node.cu):
+                                 // written by the launch that produces an h version, bulk-loaded by the launch that consumes it
     float* x_in = nullptr;       // [N][3]
     float* x_a = nullptr;        // [N][3]
     float* x_b = nullptr;        // [N][3]
@@ -284,6 +286,7 @@ struct dp_handle {
     int node_mc = 0;                   // DIFFPHAR_NODE_MC: node kernel in clusters of 2 whose weight panels arrive by TMA multicast (each CTA
                                        // fetches half of every panel for both).  Measured 3 % SLOWER (profiles/r06a_ab_summary.txt): the GEMM
                                        // phases are paced by the MMAs' own operand fetch, not by the L2 -> SM weight stream
+    int node_h16 = 1;                  // DIFFPHAR_NODE_H16: h travels between the node launches as 16-bit tile images (TMA in / out)
     int node_split = 64;               // DIFFPHAR_NODE_SPLIT: nodes per tile for the tiles that hold phar rows (one projection block more
                                        // than the rest); 0 = uniform tiles
     int trace_cta = 0;                 // DIFFPHAR_TRACE_CTA: which CTA of the traced kernel writes the timeline
@@ -378,6 +381,10 @@ int egnn_f32_init();
 // 2: pocket nodes = h_base + t * w_time (their type features are constant during sampling), phar nodes in full
 int launch_encode_nodes(dp_handle* h, const float* xh_phar, const float* xh_res, const float* t_base,
                         const int* step_idx, int row_stride, int t_stride, int base_mode, cudaStream_t st);
+// node tiles of the fused tcgen05 node kernel (tc_node.cu): the first `tp` tiles hold `sp` nodes each, the rest `stride`
+struct NodeTiling { int tp, sp, stride, grid; };
+void node_tiling(const dp_handle* h, int N, int Np, NodeTiling* t);
+size_t node_tile_image_bytes();
 int launch_coord_finish(dp_handle* h, const float* x_cur, float* x_next, int n_moving, cudaStream_t st);
 int launch_velocity_center(dp_handle* h, float* out_phar, float* out_res, cudaStream_t st);
 int launch_decode(dp_handle* h, const float* x_final, float* out_phar, float* out_res, cudaStream_t st);

@@ -106,6 +106,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// shared -> global (TMA engine); completion is tracked by the issuing THREAD's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- TMEM ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t holder_smem, uint32_t cols)
 {

@@ -59,6 +59,9 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
+#ifndef EDGE_PA_AHEAD
+#define EDGE_PA_AHEAD 1                            // how many edges ahead the producer requests the Pa row of a new CSR row run (1 or 2)
+#endif
 #ifndef EDGE_REGS_MMA
 #define EDGE_REGS_MMA 32
 #endif
@@ -326,6 +329,15 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         // edge of work instead of sitting in the chain
         int cur_row = __shfl_sync(0xffffffffu, m_row, 0);
         uint4 cur = ldg_u4(row_ptr(pa_base, (uint32_t)cur_row, ldp_b));
+#if EDGE_PA_AHEAD == 2
+        // two edges ahead: `pend` holds the Pa of the NEXT edge's row when that edge starts a new row run (pend_new), requested
+        // one edge ago; the reload for the edge after that is issued now.  At Calpha degrees (6.7 edges per row) a warp's 8
+        // edges change rows 1.2 times per tile and one edge of work (~450 cycles) does not cover an L2 round trip.
+        int row1 = __shfl_sync(0xffffffffu, m_row, 1);
+        bool pend_new = row1 != cur_row;
+        uint4 pend;
+        ldg4_if_noinit(pend, row_ptr(pa_base, (uint32_t)row1, ldp_b), pend_new);
+#endif
         unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
         const int l74 = (lane & 7) << 4;
 
@@ -353,6 +365,16 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+#if EDGE_PA_AHEAD == 2
+                const int row2 = i < 6 ? __shfl_sync(0xffffffffu, m_row, i + 2) : __shfl_sync(0xffffffffu, n_row, i - 6);
+                if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
+                const bool new2 = row2 != row1 && !(a.dbg & 2);
+                uint4 fresh2;                                                            // only read under new2 (as `pend`, two edges on)
+                ldg4_if_noinit(fresh2, row_ptr(pa_base, (uint32_t)row2, ldp_b), new2);
+                const int next_row = row1;
+                const uint4 nxt = make_uint4(pend_new ? pend.x : cur.x, pend_new ? pend.y : cur.y, pend_new ? pend.z : cur.z, pend_new ? pend.w : cur.w);
+                pend = fresh2; pend_new = new2; row1 = row2;
+#else
                 const int next_row = i < 7 ? __shfl_sync(0xffffffffu, m_row, i + 1) : __shfl_sync(0xffffffffu, n_row, 0);
                 if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
                 // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
@@ -368,6 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 ldg4_if(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
 #endif
                 const uint4 nxt = make_uint4(new_run ? fresh.x : cur.x, new_run ? fresh.y : cur.y, new_run ? fresh.z : cur.z, new_run ? fresh.w : cur.w);
+#endif
                 if (TRACE && i < 2) {                                                    // timeline only: when Pa / Pb of this edge have landed
                     uint32_t t0, t1;
                     asm volatile("mov.b32 %0, %1;" : "=r"(t0) : "r"(cur.x));

@@ -60,6 +60,11 @@ struct NodeArgs {
                                                  // rows run one projection block more than the others (Qa), so they get fewer nodes — the
                                                  // launch ends with its slowest CTA.  tp = 0: uniform tiles.  Single-CTA kernel only.
     int trace_cta;                               // which CTA writes the debug timeline
+    // 16-bit images of the h tiles (one [4 K panels][NT rows][128 B] swizzled B tile per node tile, the layout the MMAs read):
+    // a launch that produces an h version stores its new-h tile with one bulk copy per K panel (h16_out), the next launch —
+    // same tiling — brings it straight into shared memory through the TMA (h16_in) instead of loading fp32 rows through
+    // registers, converting and storing them: the compute warps start on the aggregated messages at once.
+    const unsigned char* h16_in; unsigned char* h16_out;
     int row_block; int n_moving;                 // block `row_block` (row part Qa of the coordinate MLP, -1: none) is only read for rows < n_moving
                                                  // (update_coords_mask keeps phar rows, dynamics.py:105-107): tiles past them skip it
     long long* trace;                            // debug timeline (dp_debug_trace), normally null
@@ -127,36 +132,53 @@ __device__ __forceinline__ void stage_agg(unsigned char* tile, const NodeArgs& a
 {
     const AggView& g = a.aggv;
     const int r0 = n0 + ROWS_PER_WARP * wid;
-    float4 f[ROWS_PER_WARP][2];
-    int cd[ROWS_PER_WARP];
+    // Two batches of three rows.  A row that crosses a segmented-sum boundary is the sum of its pieces in lane / unit order:
+    // with 16-edge units and ~7 edges per row (Calpha pockets) four rows in ten have a second piece, so it is requested
+    // TOGETHER with the first (one L2 round trip per batch; a dependent trip per split row before: 2.4 per warp).  Third
+    // and later pieces (a row longer than a unit) stay a rare serial loop.
+    constexpr int RB = ROWS_PER_WARP / 2;
+    static_assert(ROWS_PER_WARP % 2 == 0, "two batches");
 #pragma unroll
-    for (int u = 0; u < ROWS_PER_WARP; ++u) {                                      // all 12 loads of the warp in flight together
-        cd[u] = __shfl_sync(0xffffffffu, code, u);
-        if (r0 + u >= row_end) cd[u] = AGG_EMPTY;
-        f[u][0] = f[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cd[u] != AGG_EMPTY) {
-            const unsigned k = (unsigned)(-(cd[u] + 1));                               // split rows: first piece = partial row 2 lf + slot
-            const float* src = cd[u] >= 0 ? g.agg + (size_t)cd[u] * H : g.partials + ((size_t)(k >> 11) * 2 + (k & 1u)) * H;
-            f[u][0] = *reinterpret_cast<const float4*>(src + 8 * lane);
-            f[u][1] = *reinterpret_cast<const float4*>(src + 8 * lane + 4);
-        }
-    }
+    for (int hb = 0; hb < 2; ++hb) {
+        float4 f[RB][2], f2[RB][2];
+        int cd[RB];
 #pragma unroll
-    for (int u = 0; u < ROWS_PER_WARP; ++u) {
-        float v[8] = {f[u][0].x, f[u][0].y, f[u][0].z, f[u][0].w, f[u][1].x, f[u][1].y, f[u][1].z, f[u][1].w};
-        if (cd[u] < 0 && cd[u] != AGG_EMPTY) {                                         // warp-uniform, rare: the remaining pieces
-            const unsigned k = (unsigned)(-(cd[u] + 1)), lf = k >> 11, extra = (k >> 1) & 1023u;
-            for (unsigned i = 1; i <= extra; ++i) {
-                const float* src = g.partials + ((size_t)(lf + i) * 2) * H + 8 * lane;
-                const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
-                v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+        for (int u = 0; u < RB; ++u) {
+            const int ru = RB * hb + u;
+            cd[u] = __shfl_sync(0xffffffffu, code, ru);
+            if (r0 + ru >= row_end) cd[u] = AGG_EMPTY;
+            f[u][0] = f[u][1] = f2[u][0] = f2[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cd[u] != AGG_EMPTY) {
+                const unsigned k = (unsigned)(-(cd[u] + 1));                           // split rows: first piece = partial row 2 lf + slot
+                const float* src = cd[u] >= 0 ? g.agg + (size_t)cd[u] * H : g.partials + ((size_t)(k >> 11) * 2 + (k & 1u)) * H;
+                f[u][0] = *reinterpret_cast<const float4*>(src + 8 * lane);
+                f[u][1] = *reinterpret_cast<const float4*>(src + 8 * lane + 4);
+                if (cd[u] < 0 && ((k >> 1) & 1023u) >= 1u) {                           // warp-uniform: the second piece
+                    const float* s2 = g.partials + ((size_t)((k >> 11) + 1u) * 2) * H + 8 * lane;
+                    f2[u][0] = *reinterpret_cast<const float4*>(s2);
+                    f2[u][1] = *reinterpret_cast<const float4*>(s2 + 4);
+                }
             }
         }
-        const int deg = __shfl_sync(0xffffffffu, rp, u + 1) - __shfl_sync(0xffffffffu, rp, u);
-        const float sc = g.mean ? __fdividef(1.0f, (float)max(deg, 1)) : g.inv_norm;
-        *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + u, lane, NX_PANEL)) =
-            make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
-                       pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+            const int ru = RB * hb + u;
+            float v[8] = {f[u][0].x + f2[u][0].x, f[u][0].y + f2[u][0].y, f[u][0].z + f2[u][0].z, f[u][0].w + f2[u][0].w,
+                          f[u][1].x + f2[u][1].x, f[u][1].y + f2[u][1].y, f[u][1].z + f2[u][1].z, f[u][1].w + f2[u][1].w};
+            if (cd[u] < 0 && cd[u] != AGG_EMPTY) {                                     // warp-uniform, rare: pieces three and up
+                const unsigned k = (unsigned)(-(cd[u] + 1)), lf = k >> 11, extra = (k >> 1) & 1023u;
+                for (unsigned i = 2; i <= extra; ++i) {
+                    const float* src = g.partials + ((size_t)(lf + i) * 2) * H + 8 * lane;
+                    const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 4);
+                    v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                }
+            }
+            const int deg = __shfl_sync(0xffffffffu, rp, ru + 1) - __shfl_sync(0xffffffffu, rp, ru);
+            const float sc = g.mean ? __fdividef(1.0f, (float)max(deg, 1)) : g.inv_norm;
+            *reinterpret_cast<uint4*>(tile + chunk_offset(ROWS_PER_WARP * wid + ru, lane, NX_PANEL)) =
+                make_uint4(pack2<FMT>(v[0] * sc, v[1] * sc), pack2<FMT>(v[2] * sc, v[3] * sc),
+                           pack2<FMT>(v[4] * sc, v[5] * sc), pack2<FMT>(v[6] * sc, v[7] * sc));
+        }
     }
 }
 
@@ -193,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
 
     if (tid == 0) {
         for (int i = 0; i < N_WS; ++i) { mbar_init(smem_u32(&s.bar_wfull[i]), 1); mbar_init(smem_u32(&s.bar_wempty[i]), MC ? 2 : 1); }
-        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.bar_x[i]), COMPUTE_WARPS);
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.bar_x[i]), (i == 3 && a.h16_in) ? 1 : COMPUTE_WARPS);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bar_accfull[i]), 1); mbar_init(smem_u32(&s.bar_accempty[i]), COMPUTE_WARPS); }
         fence_barrier_init();
     }
@@ -211,6 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
         // ================================ weight stream ================================
         {
             const uint32_t w0 = warp_uniform(smem_u32(s.w[0]));
+            if (a.h16_in && a.do_mlp) {
+                // the h tile of this CTA, written by the previous node launch in the layout GEMM 1 reads: rows [0, n_mma) of each K panel
+                pdl_wait();
+                if (elect_one()) {
+                    const uint32_t bytes = (uint32_t)n_mma * 128u;
+                    mbar_expect_tx(smem_u32(&s.bar_x[3]), 4 * bytes);
+#pragma unroll
+                    for (int kp = 0; kp < 4; ++kp)
+                        bulk_g2s(smem_u32(s.xa) + kp * NX_PANEL, a.h16_in + ((size_t)cta * 4 + kp) * NX_PANEL, bytes, smem_u32(&s.bar_x[3]));
+                }
+                __syncwarp();
+            }
             int p = 0;                                                                // ring position
             for (int g = 0; g < mlp_panels + 4 * a.n_blocks; ++g) {                    // g = panel of the image
                 if (g >= mlp_panels && (g - mlp_panels) / 4 == skip_b) continue;
@@ -272,11 +306,20 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
                 run_gemm(1, xa, 0, 4);
             }
             mbar_wait(smem_u32(&s.bar_x[2]), 0);
+            if (a.h16_out && lane == 0) {                                            // the new h tile is complete (and stays: the projections only read it)
+                const uint32_t bytes = (uint32_t)n_mma * 128u;
+#pragma unroll
+                for (int kp = 0; kp < 4; ++kp) bulk_s2g(a.h16_out + ((size_t)cta * 4 + kp) * NX_PANEL, xb + kp * NX_PANEL, bytes);
+                bulk_commit_group();
+            }
+            __syncwarp();
             for (int b = 0, cnt = 0; b < a.n_blocks; ++b) {
                 if (b == skip_b) continue;
                 run_gemm(cnt & 1, xb, 0, 4);
                 ++cnt;
             }
+            if (a.h16_out && lane == 0) bulk_wait_group0();                          // the image is in global memory before the CTA ends
+            __syncwarp();
         }
     } else {
         // ================================ compute warps ================================
@@ -310,8 +353,10 @@ __global__ void __launch_bounds__(THREADS, 1) node_tc_kernel(NodeArgs a, const u
             if (lane <= ROWS_PER_WARP) rp = a.aggv.rowptr[min(n0 + ROWS_PER_WARP * wid + lane, a.n_rows)];
             int code = AGG_EMPTY;                                                    // where each row's aggregate lives
             if (lane < ROWS_PER_WARP && n0 + ROWS_PER_WARP * wid + lane < a.n_rows) code = a.aggv.src[n0 + ROWS_PER_WARP * wid + lane];
-            stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
-            publish(3);
+            if (!a.h16_in) {                                                         // else: the TMA warp brings the 16-bit tile
+                stage_h<FMT>(s.xa, a, n0, n0 + n_valid, wid, lane);
+                publish(3);
+            }
             if (tr) trace_mark(trace_p, 0, 0, 1);
             stage_agg<FMT>(s.xb, a, n0, n0 + n_valid, wid, lane, rp, code);
             publish(0);
@@ -750,6 +795,28 @@ int tc_node_init()
     return DP_OK;
 }
 
+size_t node_tile_image_bytes() { return (size_t)X_BYTES; }
+
+// Whole waves of SMs: the fewest waves that fit NT-node tiles, then the smallest stride that keeps that count.  The tiles
+// that hold phar rows (one projection block more than the rest in most launches) get h->node_split nodes each; every
+// launch of a denoiser evaluation uses the same tiling (the h images are exchanged tile by tile).
+void node_tiling(const dp_handle* h, int N, int Np, NodeTiling* t)
+{
+    const int sm = h->sm_count > 0 ? h->sm_count : 148;
+    const int waves = std::max(1, (N + NT * sm - 1) / (NT * sm));
+    int stride = (N + waves * sm - 1) / (waves * sm);
+    if (stride < 16) stride = 16;
+    t->tp = 0; t->sp = stride; t->stride = stride; t->grid = (N + stride - 1) / stride;
+    if (h->node_split && !h->joint && !h->node_pair && !h->node_mc && Np > 0 && Np < N) {
+        const int sp = std::min(stride, h->node_split), tp = (Np + sp - 1) / sp, rest = N - tp * sp;
+        const int ctas = waves * sm - tp;
+        if (rest > 0 && ctas > 0) {
+            const int sr = std::max(16, (rest + ctas - 1) / ctas);
+            if (sr <= NT) { t->tp = tp; t->sp = sp; t->stride = sr; t->grid = tp + (rest + sr - 1) / sr; }
+        }
+    }
+}
+
 // One launch per h version v: v = 0 is the projection of the embedded features; v = i + 1 runs GCL i's node
 // model and then projects the new h for its consumers.
 int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
@@ -771,22 +838,14 @@ int launch_node_tc(dp_handle* h, int v, const AggView& av, cudaStream_t st)
     a.range_flag = p.nan_flag + 2;
     DP_CHECK(h->tc->node[v].n_panels == (a.do_mlp ? 12 : 0) + 4 * a.n_blocks, DP_ERR_STATE, "tc node phase %d: image / shape mismatch", v);
     if (p.N <= 0) return DP_OK;
-    // whole waves of SMs: the fewest waves that fit NT-node tiles, then the smallest stride that keeps that count
-    const int waves = (p.N + NT * h->sm_count - 1) / (NT * h->sm_count);
-    int stride = (p.N + waves * h->sm_count - 1) / (waves * h->sm_count);
-    if (stride < 16) stride = 16;
-    a.stride = stride; a.n_mma = (stride + 15) / 16 * 16;
-    int grid = (p.N + stride - 1) / stride;
-    a.tp = 0; a.sp = stride; a.trace_cta = h->trace_cta;
-    if (h->node_split && !h->joint && !h->node_pair && !h->node_mc && a.row_block >= 0 && p.Np > 0 && p.Np < p.N) {
-        // tiles with moving rows: h->node_split nodes each; the rest of the SM waves share the remaining nodes evenly
-        const int sp = std::min(stride, h->node_split), tp = (p.Np + sp - 1) / sp, rest = p.N - tp * sp;
-        const int ctas = waves * h->sm_count - tp;
-        if (rest > 0 && ctas > 0) {
-            const int sr = std::max(16, (rest + ctas - 1) / ctas);
-            if (sr <= NT) { a.tp = tp; a.sp = sp; a.stride = sr; a.n_mma = (sr + 15) / 16 * 16; grid = tp + (rest + sr - 1) / sr; }
-        }
-    }
+    NodeTiling nt;
+    node_tiling(h, p.N, p.Np, &nt);
+    a.tp = nt.tp; a.sp = nt.sp; a.stride = nt.stride; a.n_mma = (nt.stride + 15) / 16 * 16; a.trace_cta = h->trace_cta;
+    const int grid = nt.grid;
+    // h as 16-bit tile images between the launches of one evaluation (single-CTA kernel; DIFFPHAR_NODE_H16=0: fp32 staging)
+    const bool images = h->node_h16 && !h->node_pair && !h->node_mc && p.h16;
+    a.h16_in = (images && v > 0) ? p.h16 : nullptr;
+    a.h16_out = (images && v + 1 < (int)h->tc->node.size()) ? p.h16 : nullptr;
     const unsigned char* img = h->tc->node[v].img[fmt];
     if (h->node_pair) {
         // cluster of two CTAs per pair of tiles (cta_group::2): an odd tile count gets one empty tile
