@@ -148,6 +148,7 @@ extern "C" int dp_create(const dp_config* cfg, int device, dp_handle** out)
     if (const char* m = getenv("DIFFPHAR_NODE_MC")) h->node_mc = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_SPLIT")) h->node_split = atoi(m);
     if (const char* m = getenv("DIFFPHAR_NODE_H16")) h->node_h16 = atoi(m);
+    if (const char* m = getenv("DIFFPHAR_COORD_FUSED")) h->coord_fused = atoi(m);
     if (const char* m = getenv("DIFFPHAR_TRACE_CTA")) h->trace_cta = atoi(m);
     if (const char* m = getenv("DIFFPHAR_TRACE_V")) h->trace_v = atoi(m);
     if (const char* m = getenv("DIFFPHAR_DBG")) h->dbg = atoi(m);
@@ -459,6 +460,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     cv.take(&p.deg, p.N); cv.take(&p.rowptr, p.N + 1); cv.take(&p.agg_src, p.N);
     cv.take(&p.col, ecap); cv.take(&p.erow, ecap); cv.take(&p.edst, ecap); cv.take(&p.d0, ecap); cv.take(&p.escal, ecap);
     cv.take(&p.counts, 4);
+    cv.take(&p.cpart, ((size_t)ecap / UNIT_TC + 2) * 8); cv.take(&p.cticket, p.N);
     cv.take(&p.scan_status, (size_t)p.N / 8 + 2); cv.take(&p.scan_ticket, 4);
     if (p.use_cells) {
         cv.take(&p.cell_start, (size_t)B * (CELLS_MAX + 1)); cv.take(&p.cell_nodes, p.N); cv.take(&p.cell_grid, (size_t)B * 8);
@@ -487,6 +489,7 @@ extern "C" int dp_plan(dp_handle* h, int32_t B, const int32_t* phar_counts, cons
     DP_CUDA(cudaMemcpy(p.sample_of, sample_of.data(), (size_t)p.N * sizeof(int), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemcpy(p.sample_ids, ids.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice));
     DP_CUDA(cudaMemset(p.counts, 0, 4 * sizeof(int)));
+    DP_CUDA(cudaMemset(p.cticket, 0, (size_t)p.N * sizeof(int)));             // self-resetting arrival tickets (tc_edge.cu, coordinate mode)
     DP_CUDA(cudaMemset(p.scan_ticket, 0, 4 * sizeof(int)));                   // the count pass's arrival ticket (graph.cu)
     DP_CUDA(cudaMemset(p.nan_flag, 0, 4 * sizeof(int)));
     DP_CUDA(cudaMemset(p.step_idx, 0, sizeof(int)));
@@ -683,11 +686,15 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             q.edst = p.edst; q.n_moving = n_moving; q.ecap = (int)p.Ecap; q.tma_fill = h->tma_fill; q.dbg = h->dbg; q.contig = p.seg_lanes;
             q.n_edges = n_coord_edges; q.agg = nullptr; q.partials = nullptr; q.escal = p.escal;
             q.coord = 1; q.attention = 0; q.use_tanh = c.use_tanh; q.trace = nullptr; q.range_flag = p.nan_flag + 2;
+            // tcgen05 modes: the kernel finishes the rows itself (x_next); the FFMA / TF32 kernels leave escal for coord_finish
+            const bool fused_finish = !fp32_layout && h->coord_fused && !(h->skip_mask & (4 | 8));
+            q.x_next = fused_finish ? x_next : nullptr; q.cpart = p.cpart; q.cticket = p.cticket;
+            q.norm_constant = c.norm_constant; q.coords_range = c.coords_range; q.norm_factor = c.normalization_factor; q.mean = c.aggregation_mean;
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
             // (a coordinate-mode kernel with row-owned tiles that finishes its phar rows itself — no second launch — was built,
             //  parity-green, and measured 5 % SLOWER per step; commit 5e2a79c, profiles/r05e_ab_summary.txt)
             prof_begin(h, PROF_EDGE_COORD, st);
-            rc = (h->skip_mask & 8) ? DP_OK : launch_coord_finish(h, x_cur, x_next, n_moving, st);
+            rc = ((h->skip_mask & 8) || fused_finish) ? DP_OK : launch_coord_finish(h, x_cur, x_next, n_moving, st);
             prof_end(h, st);
             if (rc) return rc;
             float* t = x_cur; x_cur = x_next; x_next = t;

@@ -242,6 +242,7 @@ struct Plan {
     float* agg = nullptr;        // [N][H]
     float* partials = nullptr;   // [max(FFMA units, lanes)][2][H]
     float* pq = nullptr;         // [N][1024] fp32 (FFMA mode) or [N][1024] f16 pre-scaled by 1/2 (tcgen05 modes)
+    float* cpart = nullptr; int* cticket = nullptr;   // in-kernel coordinate finish of the tcgen05 edge kernel (EdgeArgs::x_next)
     unsigned char* h16 = nullptr; // 16-bit copy of h as the node kernel's own swizzled B-tile images, one per node tile (tc_node.cu):
                                  // written by the launch that produces an h version, bulk-loaded by the launch that consumes it
     float* x_in = nullptr;       // [N][3]
@@ -286,6 +287,7 @@ struct dp_handle {
     int node_mc = 0;                   // DIFFPHAR_NODE_MC: node kernel in clusters of 2 whose weight panels arrive by TMA multicast (each CTA
                                        // fetches half of every panel for both).  Measured 3 % SLOWER (profiles/r06a_ab_summary.txt): the GEMM
                                        // phases are paced by the MMAs' own operand fetch, not by the L2 -> SM weight stream
+    int coord_fused = 1;               // DIFFPHAR_COORD_FUSED: the tcgen05 coordinate-mode edge kernel finishes its rows itself (no coord_finish launch)
     int node_h16 = 1;                  // DIFFPHAR_NODE_H16: h travels between the node launches as 16-bit tile images (TMA in / out)
     int node_split = 64;               // DIFFPHAR_NODE_SPLIT: nodes per tile for the tiles that hold phar rows (one projection block more
                                        // than the rest); 0 = uniform tiles
@@ -369,6 +371,13 @@ struct EdgeArgs {
     int ecap;                                        // allocated length of the per-edge arrays (speculative first-tile loads)
     float* agg; float* partials;                     // message outputs (coord == 0)
     float* escal;                                    // per-edge scalar output (coord == 1)
+    // coord == 1, tcgen05 path: the coordinate update is finished inside the kernel (x_next != null) — no second launch.
+    // Per 16-edge unit the epilogue sums coord_diff * scalar over each CSR row run; a row that lies inside one unit is
+    // written at once, a row that spans several units leaves one partial per unit in cpart[2 * unit + slot] (slot 1: the row
+    // runs on into the next unit, slot 0: it came from the previous one) and bumps cticket[row]: the unit that arrives
+    // last adds the pieces in unit order (deterministic whatever the arrival order), writes the row and clears the ticket.
+    float* x_next; float* cpart; int* cticket;
+    float norm_constant, coords_range, norm_factor; int mean;
     int coord; int attention; int use_tanh;
     long long* trace;                                // debug timeline (dp_debug_trace), normally null
     int* range_flag;                                 // tcgen05 path: sticky f16-range bits (Plan::nan_flag + 2)

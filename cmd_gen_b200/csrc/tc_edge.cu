@@ -82,6 +82,7 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     float red[EPI_WARPS][32 * RED_STRIDE];        // 40 KB: per-warp [channel pair][16 edges (+4 pad)]
     float part[2][EPI_WARPS][GROUP_EDGES];        // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][GROUP_EDGES];
+    float cstash[EPI_GROUPS][GROUP_EDGES][12];        // coordinate mode with the in-kernel finish: per edge (coord_diff[3], x_row[3], row, rowptr[row], rowptr[row + 1])
     unsigned long long bar_w;
     unsigned long long bar_wload, bar_wdone;          // a.tma_fill: weight panels landed in shared memory / copied to tensor memory
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
@@ -121,7 +122,9 @@ __device__ __forceinline__ void trace_mark_t(long long* trace, int role, int it,
 }
 #define trace_mark(tr, role, it, slot) trace_mark_t<TRACE>(tr, role, it, slot)
 
-template <int MODE, bool TRACE>
+// COORD: the coordinate mode is its own instantiation (a.coord == COORD), so the message kernel — the hot one — carries
+// neither its branches nor the registers of the in-kernel coordinate finish.
+template <int MODE, bool TRACE, bool COORD>
 __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const unsigned char* __restrict__ w_img)
 {
     constexpr int FMT = fmt_of_mode(MODE);            // operand format of the MMA
@@ -455,7 +458,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         const int ew = wid, q = ew & 3, gi = ew >> 2;
         const int c0 = 32 * q + lane, c1 = c0 + 128;                                     // this thread's two channels
         const float hb0 = 0.5f * a.b2[c0], hb1 = 0.5f * a.b2[c1];                        // SiLU(v + b) from hv = v / 2 + b / 2
-        const bool gated = a.coord || a.attention;
+        const bool gated = COORD || a.attention;
         const float wv0 = gated ? a.wv[c0] : 0.f, wv1 = gated ? a.wv[c1] : 0.f;
         static_assert(H == 256, "segment stores shift by 8");
         float* out0 = a.agg + c0;                                                        // [agg rows | partial rows], see graph.cu edge_dst
@@ -470,7 +473,30 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             const int ts = it % N_TS;
             const int u0 = (unit0 + it * unit_step) * UNIT_TC;                           // first edge of this group's unit
             const bool has_unit = it < n_units;                                          // shorter lanes idle through the CTA's last tile
-            const int my_dst = (!a.coord && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
+            const int my_dst = (!COORD && has_unit && lane < GROUP_EDGES && u0 + lane < E) ? a.edst[u0 + lane] : -1;
+            const bool finish = COORD && a.x_next != nullptr;
+            if (finish && q == 0) {
+                // geometry of the unit's edges, fetched while the tile is still in the pipeline (two dependent L2 trips that
+                // nobody waits for) and parked in shared memory so that no register stays live across the epilogue's hot part
+                float* st = s.cstash[gi][lane & (GROUP_EDGES - 1)];
+                int r = -1 - lane, rs = 0, re = 0;
+                float cx = 0.f, cy = 0.f, cz = 0.f, x0 = 0.f, x1 = 0.f, x2 = 0.f;
+                if (has_unit && lane < GROUP_EDGES && u0 + lane < E) {
+                    r = a.erow[u0 + lane];
+                    const int c = a.ecol[u0 + lane];
+                    x0 = a.x[3 * r]; x1 = a.x[3 * r + 1]; x2 = a.x[3 * r + 2];
+                    rs = a.rowptr[r]; re = a.rowptr[r + 1];
+                    const float dx = x0 - a.x[3 * c], dy = x1 - a.x[3 * c + 1], dz = x2 - a.x[3 * c + 2];
+                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    const float nrm = __fadd_rn(__fsqrt_rn(__fadd_rn(r2, 1e-8f)), a.norm_constant);      // coord2diff, egnn_new.py:265-270
+                    cx = __fdiv_rn(dx, nrm); cy = __fdiv_rn(dy, nrm); cz = __fdiv_rn(dz, nrm);
+                }
+                if (lane < GROUP_EDGES) {
+                    st[0] = cx; st[1] = cy; st[2] = cz; st[3] = x0; st[4] = x1; st[5] = x2;
+                    st[6] = __int_as_float(r); st[7] = __int_as_float(rs); st[8] = __int_as_float(re);
+                }
+                __syncwarp();
+            }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 0);
             mbar_wait_relaxed<EDGE_EPILOGUE_SLEEP_NS>(smem_u32(&s.bar_tfull[ts]), (it / N_TS) & 1);
             tc_fence_after();
@@ -524,11 +550,55 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 5);
                 const float tot = a.bv + ((s.part[pbuf][4 * gi][l16] + s.part[pbuf][4 * gi + 1][l16]) +
                                           (s.part[pbuf][4 * gi + 2][l16] + s.part[pbuf][4 * gi + 3][l16]));
-                if (a.coord) gate = a.use_tanh ? tanhf(tot) : tot;                       // egnn_new.py:90-93
+                if (COORD) gate = a.use_tanh ? tanhf(tot) : tot;                         // egnn_new.py:90-93
                 else gate = sigmoid_fast(tot);                                           // egnn_new.py:26-29
             }
             if (q == 0 && lane == 0) trace_mark(a.trace, 2 + gi, it, 6);
-            if (a.coord) {
+            if (finish) {
+                if (q == 0) {
+                    // trans = coord_diff * scalar (* range), summed over each CSR row run of the unit in edge order (egnn_new.py:91-103)
+                    const float* st = s.cstash[gi][lane & (GROUP_EDGES - 1)];
+                    const bool live = lane < GROUP_EDGES;
+                    const int row = live ? __float_as_int(st[6]) : -1 - lane;
+                    float tx = 0.f, ty = 0.f, tz = 0.f;
+                    if (live && row >= 0) {
+                        tx = __fmul_rn(st[0], gate); ty = __fmul_rn(st[1], gate); tz = __fmul_rn(st[2], gate);
+                        if (a.use_tanh) { tx = __fmul_rn(tx, a.coords_range); ty = __fmul_rn(ty, a.coords_range); tz = __fmul_rn(tz, a.coords_range); }
+                    }
+                    float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+                    for (int j = 0; j < GROUP_EDGES; ++j) {
+                        const int rj = __shfl_sync(0xffffffffu, row, j);
+                        const float vx = __shfl_sync(0xffffffffu, tx, j), vy = __shfl_sync(0xffffffffu, ty, j), vz = __shfl_sync(0xffffffffu, tz, j);
+                        if (j <= lane && rj == row) { sx = __fadd_rn(sx, vx); sy = __fadd_rn(sy, vy); sz = __fadd_rn(sz, vz); }
+                    }
+                    const int row_after = __shfl_sync(0xffffffffu, row, (lane + 1) & 31);
+                    if (live && row >= 0 && (lane == GROUP_EDGES - 1 || row_after != row)) {                 // last edge of a row run: its sum is complete
+                        const int rs = __float_as_int(st[7]), re = __float_as_int(st[8]);
+                        const float d = a.mean ? (float)max(re - rs, 1) : a.norm_factor;
+                        float* xo = a.x_next + 3 * (size_t)row;
+                        if (rs >= u0 && re <= u0 + GROUP_EDGES) {                                            // the whole row lies in this unit
+                            xo[0] = __fadd_rn(st[3], __fdiv_rn(sx, d)); xo[1] = __fadd_rn(st[4], __fdiv_rn(sy, d)); xo[2] = __fadd_rn(st[5], __fdiv_rn(sz, d));
+                        } else {
+                            const int un = u0 / GROUP_EDGES, fu = rs / GROUP_EDGES, lu = (re - 1) / GROUP_EDGES;
+                            float* cp = a.cpart + ((size_t)un * 2 + (un == fu ? 1 : 0)) * 4;
+                            __stcg(cp, sx); __stcg(cp + 1, sy); __stcg(cp + 2, sz);
+                            __threadfence();
+                            if (atomicAdd(a.cticket + row, 1) == lu - fu) {                                  // every other unit of the row has arrived
+                                __threadfence();
+                                float ax = 0.f, ay = 0.f, az = 0.f;
+                                for (int t = fu; t <= lu; ++t) {
+                                    const float* pp = a.cpart + ((size_t)t * 2 + (t == fu ? 1 : 0)) * 4;
+                                    ax = __fadd_rn(ax, __ldcg(pp)); ay = __fadd_rn(ay, __ldcg(pp + 1)); az = __fadd_rn(az, __ldcg(pp + 2));
+                                }
+                                xo[0] = __fadd_rn(st[3], __fdiv_rn(ax, d)); xo[1] = __fadd_rn(st[4], __fdiv_rn(ay, d)); xo[2] = __fadd_rn(st[5], __fdiv_rn(az, d));
+                                a.cticket[row] = 0;
+                            }
+                        }
+                    }
+                    __syncwarp();                                                                            // cstash is rewritten next tile
+                }
+            } else if (COORD) {
                 if (q == 0 && has_unit && lane < GROUP_EDGES && u0 + lane < E) a.escal[u0 + lane] = gate;
             } else {
                 // segmented sum over the unit's edges: thread = channel pair, registers = edges (two FMA chains)
@@ -572,8 +642,9 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 template <int MODE>
 static int edge_set_smem(int smem)
 {
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DP_CUDA(cudaFuncSetAttribute(edge_tc_kernel<MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return DP_OK;
 }
 
@@ -591,8 +662,9 @@ int tc_edge_init()
 template <int MODE>
 static cudaError_t edge_launch(dp_handle* h, const EdgeArgs& a, const unsigned char* img, int grid, int smem, cudaStream_t st)
 {
-    if (a.trace) return launch_kernel(h->pdl, edge_tc_kernel<MODE, true>, dim3(grid), dim3(THREADS), smem, st, a, img);
-    return launch_kernel(h->pdl, edge_tc_kernel<MODE, false>, dim3(grid), dim3(THREADS), smem, st, a, img);
+    if (a.coord) return launch_kernel(h->pdl, edge_tc_kernel<MODE, false, true>, dim3(grid), dim3(THREADS), smem, st, a, img);
+    if (a.trace) return launch_kernel(h->pdl, edge_tc_kernel<MODE, true, false>, dim3(grid), dim3(THREADS), smem, st, a, img);
+    return launch_kernel(h->pdl, edge_tc_kernel<MODE, false, false>, dim3(grid), dim3(THREADS), smem, st, a, img);
 }
 
 int launch_edge_tc(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st)

@@ -27,16 +27,17 @@ DEV = "cuda:0"
 CASES = ["ca_small", "fa_small", "nocut", "mean_agg"]
 
 
-def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, node_mc=None, node_split=None, node_h16=None):
+def make_handle(cfg, wseed, precision="fp32", graph=None, seg=None, node_pair=None, tma_fill=None, node_mc=None, node_split=None, node_h16=None, coord_fused=None):
     """graph: None = automatic choice, "scan" / "cells" force one of the two radius-graph builders (DIFFPHAR_GRAPH; "fused" = the scan
     as one launch with a look-back prefix);
     seg: None = automatic, "units" / "lanes" force a segmented-sum scheme of the tcgen05 edge kernel (DIFFPHAR_SEG);
     node_pair="1": the CTA-pair (cta_group::2) node kernel; tma_fill="0": the load / store weight fill of the edge kernel;
     node_mc="1": node kernel in clusters of two sharing one multicast weight stream; node_split="0": uniform node tiles;
-    node_h16="0": h staged from fp32 rows instead of the 16-bit tile images."""
+    node_h16="0": h staged from fp32 rows instead of the 16-bit tile images; coord_fused="0": separate coord_finish launch."""
     import os
     forced = {"DIFFPHAR_GRAPH": graph, "DIFFPHAR_SEG": seg, "DIFFPHAR_NODE_PAIR": node_pair, "DIFFPHAR_TMA_FILL": tma_fill,
-              "DIFFPHAR_NODE_MC": node_mc, "DIFFPHAR_NODE_SPLIT": node_split, "DIFFPHAR_NODE_H16": node_h16}
+              "DIFFPHAR_NODE_MC": node_mc, "DIFFPHAR_NODE_SPLIT": node_split, "DIFFPHAR_NODE_H16": node_h16,
+              "DIFFPHAR_COORD_FUSED": coord_fused}
     old = {k: os.environ.pop(k, None) for k in forced}
     for k, v in forced.items():
         if v:
@@ -380,7 +381,8 @@ def test_segmented_sum_schemes_agree(label, sizes, counts, res_nf, density, seg)
 
 @pytest.mark.parametrize("switch", [{"node_pair": "1"}, {"tma_fill": "0"}, {"node_pair": "1", "seg": "lanes"},
                                     {"node_mc": "1"}, {"node_split": "0"}, {"node_split": "32"}, {"node_mc": "1", "seg": "lanes"},
-                                    {"node_h16": "0"}, {"node_h16": "0", "node_split": "0"}])
+                                    {"node_h16": "0"}, {"node_h16": "0", "node_split": "0"}, {"coord_fused": "0"},
+                                    {"coord_fused": "0", "seg": "lanes"}])
 def test_alternative_kernel_paths_match_the_default(switch):
     """The switchable kernel variants kept for A/B runs (CTA-pair node kernel with tcgen05 cta_group::2 and DSMEM bulk
     exchange; LDG + tcgen05.st weight fill of the edge kernel) against the default path on a ragged batch: same
