@@ -693,10 +693,12 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
             if ((rc = run_edge(h, q, 4 * G + b, st))) return rc;
             // (a coordinate-mode kernel with row-owned tiles that finishes its phar rows itself — no second launch — was built,
             //  parity-green, and measured 5 % SLOWER per step; commit 5e2a79c, profiles/r05e_ab_summary.txt)
-            prof_begin(h, PROF_EDGE_COORD, st);
-            rc = ((h->skip_mask & 8) || fused_finish) ? DP_OK : launch_coord_finish(h, x_cur, x_next, n_moving, st);
-            prof_end(h, st);
-            if (rc) return rc;
+            if (!fused_finish && !(h->skip_mask & 8)) {
+                prof_begin(h, PROF_EDGE_COORD, st);
+                rc = launch_coord_finish(h, x_cur, x_next, n_moving, st);
+                prof_end(h, st);
+                if (rc) return rc;
+            }
             float* t = x_cur; x_cur = x_next; x_next = t;
         }
     }

@@ -34,6 +34,13 @@ def main():
             out, fp, fk = h.sample(xh.clone(), noise=None, seed=5, return_frames=2, norm=(1.0, 4.0, 0.0))
             torch.cuda.synchronize()
             fl = h.flags()
+            # joint mode (update_pocket_coords=True): the coordinate kernel covers every edge and finishes every row
+            h.set_update_pocket_coords(True)
+            n_p = sum(counts)
+            zj = torch.cat([xh[:n_p, :3] + 1.0, torch.zeros(n_p, cfg.phar_nf, device="cuda")], 1).contiguous()
+            jp, jr = h.dynamics_forward(zj, xh, torch.full((len(counts),), 0.3))
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(jp).all()) and bool(torch.isfinite(jr).all())
             print(prec, seg, graph, "E", fl.last_n_edges, "finite", bool(torch.isfinite(out).all()), "launches", h.launch_count(), flush=True)
             del h
 
