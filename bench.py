@@ -12,6 +12,10 @@ N = 10 112 nodes, E ~ 68 k directed edges, random-init weights of crossdocked_ca
 With N ranks every rank runs its own batch (weak scaling, no collective in the loop) and
 the sampled point clouds are all-gathered once per run.
 
+Kernel times behind the rooflines are CUDA events around every launch, recorded as NODES of the captured step graph and
+read after each of 20 replays (`roofline.timing`); the same spans around eager launches (`*_eager`) and the message
+kernel repeated 8x inside one event pair (`roofline.back_to_back`, informational) stand beside them.
+
 Beside the headline line's `value` / `e2e` / `roofline` / `cpu_baseline` the same JSON line carries
   roofline_node : the fused node kernel against the tensor roofline (FLOPs of the node MLP + the factored first layers)
   rooflines     : K1 graph build, K3 coordinate path, K4 DDPM update against the HBM roofline (all latency-bound here)
@@ -278,17 +282,23 @@ def timed_runs(fn, n_warm, n_timed, dev, flush=None):
     return total / n_timed
 
 
-def profile_families(h, xh_dev0, noise_dev, n_prof):
-    """Per-family kernel times of n_prof eager denoising steps (CUDA events around every launch)."""
+def profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=True):
+    """Per-family kernel times of n_prof denoising steps, CUDA events around every launch.
+    in_graph=True : the events are event-record NODES of the captured step graph (the production graph, replayed
+                    n_prof times, read after every replay) — launch durations where they count, between the dependent
+                    kernels of the timed loop; the stand-alone final evaluation is not instrumented (calls = n_prof);
+    in_graph=False: eager launches, one event pair per launch (calls = n_prof + 1): every span also holds the idle front
+                    end of a launch into an empty stream (~4-6 us), which no graph replay pays.
+    Returns (prof, flags, calls)."""
     tab_p = step_table(gamma_table("polynomial_2", 500, 1e-5), 500, n_prof)
     h.set_step_table(tab_p.rows, tab_p.final)
     noise_p = noise_dev[: n_prof + 2].contiguous()
-    h.profile_enable(True)
+    h.profile_enable(in_graph if isinstance(in_graph, int) and not isinstance(in_graph, bool) else (2 if in_graph else 1))
     h.sample(xh_dev0.clone(), noise_p)
     names = ["edge_msg", "node_linear", "edge_coord", "graph_build", "ddpm", "other"]
     prof = {n: h.profile_read(i) for i, n in enumerate(names)}
     h.profile_enable(False)
-    return prof, h.flags()
+    return prof, h.flags(), (n_prof if in_graph else n_prof + 1)
 
 
 def side_workload(name, dev, precision, flush, n_samples=None, timesteps=500, full_run=True):
@@ -311,13 +321,13 @@ def side_workload(name, dev, precision, flush, n_samples=None, timesteps=500, fu
     fl = h.flags()
     assert fl.edge_overflow == 0
     n_prof = min(10, steps)
-    prof, flp = profile_families(h, xh_dev0, noise_dev, n_prof)
+    prof_e, _, _ = profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=False)
+    prof, flp, calls = profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=True)
     N, E = n_p + B * w["n_res"], int(flp.last_n_edges)
     msg_ms, msg_n = prof["edge_msg"]
     node_ms, node_n = prof["node_linear"]
     hbm, tens, src = measured_peaks()
     ach = algorithmic_bytes_msg(N, E) / (msg_ms / max(msg_n, 1) * 1e-3) / 1e9
-    calls = n_prof + 1
     node_tf = node_flops_per_call(N, w["n_layers"]) * calls / (node_ms * 1e-3) / 1e12
     step_us = ms * 1e3 / (steps + 1)
     out = {"workload": w["label"].replace("x %d samples" % WORKLOADS[name]["n_samples"], "x %d samples" % B),
@@ -326,6 +336,7 @@ def side_workload(name, dev, precision, flush, n_samples=None, timesteps=500, fu
            "timed": "one full %d-step run" % timesteps if full_run else "20 denoising steps, extrapolated x%d" % (timesteps + 1),
            "roofline": {"bound": "hbm", "kernel": "edge message kernel", "achieved": ach, "peak": hbm, "unit": "GB/s",
                         "frac": ach / hbm, "avg_launch_us": msg_ms / max(msg_n, 1) * 1e3,
+                        "avg_launch_us_eager": prof_e["edge_msg"][0] / max(prof_e["edge_msg"][1], 1) * 1e3,
                         "bytes_per_launch": algorithmic_bytes_msg(N, E)},
            "roofline_node": {"bound": "tensor", "kernel": "fused node kernel", "achieved": node_tf, "peak": tens,
                              "unit": "TFLOP/s", "frac": node_tf / tens, "avg_launch_us": node_ms / max(node_n, 1) * 1e3},
@@ -471,9 +482,12 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    # ---- rooflines, timed live with CUDA events around every launch of 21 eager denoiser evaluations ---
+    # ---- rooflines, timed live with CUDA events around every launch: inside the replayed step graph (primary) and around
+    # eager launches (kept beside it: what round 1 reported) -------------------------------------------------------------
     n_prof = min(20, args.timesteps)
-    prof, flp = profile_families(h, xh_dev0, noise_dev, n_prof)
+    prof_e, _, calls_e = profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=False)
+    prof, flp, calls = profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=True)
+    prof_b, _, _ = profile_families(h, xh_dev0, noise_dev, n_prof, in_graph=3)     # message spans hold 8 back-to-back launches
     h.set_step_table(tab.rows, tab.final)
     N = n_p + B * WORKLOAD["n_res"]
     E, Ep = int(flp.last_n_edges), int(flp.last_n_edges_phar)
@@ -490,9 +504,9 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(open(tfile)).get(args.workload, {}).get(args.precision)
         except Exception:
             traffic = None
-    calls = n_prof + 1
     node_ms, node_n = prof["node_linear"]
     node_tf = node_flops_per_call(N, WORKLOAD["n_layers"]) * calls / (node_ms * 1e-3) / 1e12 if node_ms else 0.0
+    step_us_now = total_ms / args.steps * 1e3 / (args.timesteps + 1)
 
     def hbm_entry(kernel, per_call_bytes, fam):
         ms, n = prof[fam]
@@ -524,15 +538,29 @@ def run_ours(args, rank, world, local_rank):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture "
                                        "summarised in profiles/ (profiles/edge_msg_traffic.json names the file)",
                      "bytes_per_launch": bytes_launch, "avg_launch_us": avg_ms * 1e3, "launches_timed": msg_n,
-                     "share_of_step": msg_ms / tot_prof if tot_prof else None,
+                     "timing": "CUDA events recorded as nodes of the captured step graph, around every launch of %d replays "
+                               "(the loop the headline times); avg_launch_us_eager = the same kernel between events around an "
+                               "eager launch, which also holds the idle front end of a launch into an empty stream" % calls,
+                     "avg_launch_us_eager": prof_e["edge_msg"][0] / max(prof_e["edge_msg"][1], 1) * 1e3,
+                     "frac_eager": bytes_launch / (prof_e["edge_msg"][0] / max(prof_e["edge_msg"][1], 1) * 1e-3) / 1e9 / peak,
+                     "back_to_back": {"launches_per_event_pair": 8,
+                                      "avg_launch_us": prof_b["edge_msg"][0] / max(prof_b["edge_msg"][1], 1) / 8 * 1e3,
+                                      "frac": bytes_launch / (prof_b["edge_msg"][0] / max(prof_b["edge_msg"][1], 1) / 8 * 1e-3) / 1e9 / peak,
+                                      "note": "informational: the same message launch repeated 8 times between ONE event pair (eager, "
+                                              "same inputs, L2-resident as in the loop) amortises the event pair's own ~5 us; the sum "
+                                              "of the single-launch spans of a step exceeds the step itself by about a third"},
+                     "share_of_step": msg_ms * 1e3 / calls / step_us_now,
                      "kernel_ms_by_kind": {k: v[0] for k, v in prof.items()},
+                     "kernel_ms_by_kind_eager": {k: v[0] for k, v in prof_e.items()},
+                     "denoiser_calls_timed": calls,
                      "note": ("working set (~30 MB) is L2-resident at this size: latency-bound, not HBM-bound"
                               if args.workload == "config2" else "steady state: >100 tiles per CTA")},
         "roofline_node": {"bound": "tensor", "kernel": "fused node kernel (node MLP + factored first layers of the next edge / coordinate MLP)",
                           "achieved": node_tf, "peak": peak_tensor, "unit": "TFLOP/s", "frac": node_tf / peak_tensor,
                           "flops_per_denoiser_call": node_flops_per_call(N, WORKLOAD["n_layers"]),
                           "us_per_denoiser_call": node_ms * 1e3 / calls, "avg_launch_us": node_ms * 1e3 / max(node_n, 1),
-                          "share_of_step": node_ms / tot_prof if tot_prof else None},
+                          "avg_launch_us_eager": prof_e["node_linear"][0] * 1e3 / max(prof_e["node_linear"][1], 1),
+                          "share_of_step": node_ms * 1e3 / calls / step_us_now},
         "rooflines": [hbm_entry("K1 radius graph -> CSR", algorithmic_bytes_graph(N, E), "graph_build"),
                       hbm_entry("K3 coordinate update (phar rows)", WORKLOAD["n_layers"] * algorithmic_bytes_coord(n_p, Ep), "edge_coord"),
                       hbm_entry("K4 DDPM update", algorithmic_bytes_ddpm(n_p, B * WORKLOAD["n_res"]), "ddpm")],

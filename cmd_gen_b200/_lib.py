@@ -289,7 +289,9 @@ class Handle:
     def launch_count(self) -> int:
         return int(self.lib.dp_launch_count(self.h))
 
-    def profile_enable(self, on: bool):
+    def profile_enable(self, on):
+        """on: False / True = CUDA events around every EAGER launch; 2 = events recorded inside the captured step graph
+        (external event-record nodes, read after every replay): launch durations in the production context."""
         _check(self.lib.dp_profile_enable(self.h, int(on)))
 
     def profile_read(self, which: int):

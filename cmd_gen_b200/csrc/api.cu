@@ -42,16 +42,32 @@ extern "C" int dp_device_count(void)
 void prof_begin(dp_handle* h, int which, cudaStream_t st)
 {
     if (!h->profile || h->spans.size() > 60000) return;
+    if (h->profile == 2 && !h->capturing) return;              // in-graph mode: only the captured step is instrumented
     dp_handle::Span s; s.which = which;
     cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-    cudaEventRecord(s.a, st);
+    if (h->profile == 2) cudaEventRecordWithFlags(s.a, st, cudaEventRecordExternal);   // an event-record NODE of the graph
+    else cudaEventRecord(s.a, st);
     h->spans.push_back(s);
 }
 
 void prof_end(dp_handle* h, cudaStream_t st)
 {
     if (!h->profile || h->spans.empty()) return;
-    cudaEventRecord(h->spans.back().b, st);
+    if (h->profile == 2 && !h->capturing) return;
+    if (h->profile == 2) cudaEventRecordWithFlags(h->spans.back().b, st, cudaEventRecordExternal);
+    else cudaEventRecord(h->spans.back().b, st);
+}
+
+// in-graph mode: the spans' events were re-recorded by the replay that just finished on `st`
+static int prof_collect_replay(dp_handle* h, cudaStream_t st)
+{
+    DP_CUDA(cudaStreamSynchronize(st));
+    for (auto& s : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { h->prof_ms[s.which] += ms; h->prof_n[s.which] += 1; }
+    }
+    cudaGetLastError();
+    return DP_OK;
 }
 
 // --------------------------------------------------------------------------------------
@@ -582,7 +598,12 @@ static int run_edge(dp_handle* h, const EdgeArgs& a, int lin_id, cudaStream_t st
 {
     if (h->skip_mask & (a.coord ? 4 : 1)) return DP_OK;
     prof_begin(h, a.coord ? PROF_EDGE_COORD : PROF_EDGE_MSG, st);
-    int rc = h->precision == DP_TF32 ? launch_edge_tf32(h, a, lin_id, st)
+    // profile mode 3: the message kernel (a pure function of its inputs) runs DP_PROFILE_REPEAT times back to back inside
+    // one event pair, so the pair's own cost (~5 us: a span around ONE 20 us kernel overstates it by a quarter) is amortised
+    const int reps = (h->profile == 3 && !a.coord) ? DP_PROFILE_REPEAT : 1;
+    int rc = DP_OK;
+    for (int r = 0; r < reps && !rc; ++r)
+        rc = h->precision == DP_TF32 ? launch_edge_tf32(h, a, lin_id, st)
              : (h->precision == DP_FP32 || !(h->tc_mask & 1)) ? launch_edge_f32(h, a, st) : launch_edge_tc(h, a, lin_id, st);
     prof_end(h, st);
     return rc;
@@ -604,7 +625,7 @@ static int run_denoiser(dp_handle* h, const float* xh_phar, const float* xh_res,
     // (the side stream joins the capture through the event).  Profiling spans need one stream: no fork then.
     // In the sampler (pocket_base) the coordinates were already written by the previous DDPM update, so the branch
     // starts BEFORE the encoder; a stand-alone evaluation gets them from the encoder and forks after it.
-    const bool fork = !h->profile && !(h->skip_mask & 16);
+    const bool fork = (h->profile == 0 || h->profile == 2) && !(h->skip_mask & 16);
     const bool early = fork && pocket_base && !(h->dbg & 32);             // dbg bit 5: fork after the encoder (A/B)
     if (early) {
         DP_CUDA(cudaEventRecord(h->ev_fork, st));
@@ -787,11 +808,16 @@ static int sample_core(dp_handle* h, const FrameSpec& fs, cudaStream_t st)
     d0.x_in = p.x_in; d0.x_a = p.x_a; d0.x_b = p.x_b;
     if ((rc = launch_ddpm(h, d0, st))) return rc;
 
-    if (h->profile) {
+    if (h->profile == 1 || h->profile == 3) {
         for (int k = 0; k < h->n_steps; ++k)
             if ((rc = sampler_step_launches(h, pocket, noise, fs, st))) return rc;
     } else {
         const int want_frames = fs.return_frames > 1 ? fs.return_frames : 0;
+        if (h->profile == 2) {                                    // the instrumented graph is captured afresh (and dropped afterwards)
+            drop_graph(h);
+            for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+            h->spans.clear();
+        }
         if (!h->step_graph || h->graph_precision != h->precision || h->graph_frames != want_frames) {
             drop_graph(h);
             const int64_t before = h->launches;
@@ -800,7 +826,9 @@ static int sample_core(dp_handle* h, const FrameSpec& fs, cudaStream_t st)
             // replay the instantiated graph on the caller's stream
             if (!h->capture_stream) DP_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
             DP_CUDA(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+            h->capturing = true;
             rc = sampler_step_launches(h, pocket, noise, fs, h->capture_stream);
+            h->capturing = false;
             cudaError_t ce = cudaStreamEndCapture(h->capture_stream, &g);
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             DP_CUDA(ce);
@@ -811,8 +839,12 @@ static int sample_core(dp_handle* h, const FrameSpec& fs, cudaStream_t st)
             h->graph_precision = h->precision; h->graph_frames = want_frames;
             h->graph_captures += 1;
         }
-        for (int k = 0; k < h->n_steps; ++k) DP_CUDA(cudaGraphLaunch(h->step_graph, st));
+        for (int k = 0; k < h->n_steps; ++k) {
+            DP_CUDA(cudaGraphLaunch(h->step_graph, st));
+            if (h->profile == 2 && (rc = prof_collect_replay(h, st))) return rc;
+        }
         h->launches += h->graph_launches * h->n_steps;
+        if (h->profile == 2) drop_graph(h);
     }
     // p(x | z0): conditional_model.py:108-131
     DP_CUDA(cudaMemcpyAsync(p.t_const, &h->final_host[0], sizeof(float), cudaMemcpyHostToDevice, st));
@@ -1014,7 +1046,8 @@ extern "C" int64_t dp_launch_count(const dp_handle* h) { return h ? h->launches 
 extern "C" int dp_profile_enable(dp_handle* h, int32_t on)
 {
     DP_CHECK(h, DP_ERR_INVALID, "null handle");
-    h->profile = on != 0;
+    h->profile = (on == 2 || on == 3) ? on : (on != 0 ? 1 : 0);
+    if (!on) { for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); } h->spans.clear(); }
     if (on) {
         for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
         h->spans.clear();
@@ -1027,7 +1060,7 @@ extern "C" int dp_profile_read(dp_handle* h, int32_t which, double* total_ms, in
 {
     DP_CHECK(h && which >= 0 && which < 8, DP_ERR_INVALID, "dp_profile_read: bad argument");
     DP_CUDA(cudaSetDevice(h->device));
-    if (!h->spans.empty()) {
+    if (!h->spans.empty() && h->profile != 2) {
         DP_CUDA(cudaDeviceSynchronize());
         for (auto& s : h->spans) {
             float ms = 0.f;

@@ -327,13 +327,18 @@ struct dp_handle {
     int trace_kernel = 0;              // DIFFPHAR_TRACE: 1 = node kernel, 2 = edge message kernel
     long long* trace = nullptr;        // debug: per-role clock64 timeline of CTA 0 of the tcgen05 kernels (DIFFPHAR_TRACE=1)
     // profiling
-    bool profile = false;
+    int profile = 0;                   // dp_profile_enable: 1 = eager launches, CUDA events around every launch; 2 = the events are recorded
+                                       // INSIDE the captured step graph (external event-record nodes) and read after every replay:
+                                       // launch durations in the production context, without the idle front end of an eager launch
+    // 3 = as 1, with every message-kernel span holding DP_PROFILE_REPEAT back-to-back launches of the same kernel
+    bool capturing = false;            // between cudaStreamBeginCapture / EndCapture of the step graph
     struct Span { int which; cudaEvent_t a, b; };
     std::vector<Span> spans;
     double prof_ms[8] = {0};
     int64_t prof_n[8] = {0};
 };
 
+constexpr int DP_PROFILE_REPEAT = 8;
 enum ProfWhich { PROF_EDGE_MSG = 0, PROF_NODE = 1, PROF_EDGE_COORD = 2, PROF_GRAPH = 3, PROF_DDPM = 4, PROF_OTHER = 5 };
 
 // ---------------------------------------------------------------------------
