@@ -46,6 +46,7 @@ constexpr int X_PANEL_BYTES = TILE * 128;         // 8 KB
 constexpr int X_TILE_BYTES = 4 * X_PANEL_BYTES;   // 32 KB: 64 edges x 256 K x 2 B
 constexpr int N_XS = 4;                           // activation stages
 constexpr int N_TS = 2;                           // accumulator stages
+constexpr int N_MS = 4;                           // metadata slots (EDGE_PREP_WARP)
 constexpr int TS_COLS = 2 * TILE;                 // TMEM columns per accumulator stage
 constexpr int W_COLS = 256;                       // TMEM columns of the resident weights: half hh at hh * 128, K pair j at column j
 constexpr int TMEM_COLS = 512;
@@ -59,11 +60,15 @@ constexpr int THREADS = (EPI_WARPS + PRO_WARPS + 4) * 32;   // 7 warpgroups: 4 e
 // its own warps released.
 // The packed-f16 producer would fit in 88 registers (72 for the epilogue warps then): measured 1 % slower than 104 / 64
 // (scripts/gpu_env_ab.sh with -DEDGE_REGS_PACKED_* builds), so every mode uses the same split.
+#ifndef EDGE_PREP_WARP
+#define EDGE_PREP_WARP 0                           // 1: a warp of the MMA warpgroup prepares the tiles' edge metadata (row, col, packed
+                                                  // (r2, d0)) in shared memory, a few tiles ahead; 0: every producer warp fetches its own
+#endif
 #ifndef EDGE_PA_AHEAD
 #define EDGE_PA_AHEAD 1                            // how many edges ahead the producer requests the Pa row of a new CSR row run (1 or 2)
 #endif
 #ifndef EDGE_REGS_MMA
-#define EDGE_REGS_MMA 32
+#define EDGE_REGS_MMA (EDGE_PREP_WARP ? 40 : 32)
 #endif
 constexpr int REGS_MMA = EDGE_REGS_MMA;                      // spills ~20 registers around the once-per-launch weight fill (tcgen05.cp descriptors): harmless;
                                                   // 40 (no spill) left the producers' setmaxnreg.inc no slack and measured no faster
@@ -82,7 +87,10 @@ struct EdgeSmem {                                 // offsets from a 1024-aligned
     float red[EPI_WARPS][32 * RED_STRIDE];        // 40 KB: per-warp [channel pair][16 edges (+4 pad)]
     float part[2][EPI_WARPS][GROUP_EDGES];        // per-warp partial gate sums, double-buffered over tiles
     float gate[EPI_WARPS][GROUP_EDGES];
-    float cstash[EPI_GROUPS][GROUP_EDGES][12];        // coordinate mode with the in-kernel finish: per edge (coord_diff[3], x_row[3], row, rowptr[row], rowptr[row + 1])
+    float cstash[EPI_GROUPS][GROUP_EDGES][12];
+    // EDGE_PREP_WARP: metadata of N_MS tiles, written by the prep warp, read by the producers (broadcast LDS)
+    struct Meta { int row[TILE]; int col[TILE]; uint32_t rd[TILE]; float r2[TILE]; float d0[TILE]; } meta[4];
+    unsigned long long bar_mfull[4], bar_mempty[4];        // coordinate mode with the in-kernel finish: per edge (coord_diff[3], x_row[3], row, rowptr[row], rowptr[row + 1])
     unsigned long long bar_w;
     unsigned long long bar_wload, bar_wdone;          // a.tma_fill: weight panels landed in shared memory / copied to tensor memory
     unsigned long long bar_full[N_XS], bar_xempty[N_XS];
@@ -112,13 +120,19 @@ __device__ __forceinline__ void unpack8(const float4& a, const float4& b, float 
 }
 
 // debug timeline: role 0 = producer warp 0, 1 = MMA thread, 2 = epilogue warp 0; one CTA (phar-row lanes: CTA 0; pocket rows: 100)
+#ifndef TRACE_MARKS
+#define TRACE_MARKS 1                             // 0: the traced build keeps only the per-CTA global-timer stamps (production code otherwise)
+#endif
+#ifndef TRACE_EDGES
+#define TRACE_EDGES 0                             // 1: per-edge marks of the first two edges of a tile (they serialise the edges: coarse marks then lie)
+#endif
 #ifndef TRACE_CTA
 #define TRACE_CTA 100
 #endif
 template <bool TRACE>
 __device__ __forceinline__ void trace_mark_t(long long* trace, int role, int it, int slot)
 {
-    if (TRACE) { if (blockIdx.x == TRACE_CTA && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64(); }
+    if (TRACE && TRACE_MARKS) { if (blockIdx.x == TRACE_CTA && it < 64) trace[(role * 64 + it) * 16 + slot] = clock64(); }
 }
 #define trace_mark(tr, role, it, slot) trace_mark_t<TRACE>(tr, role, it, slot)
 
@@ -137,6 +151,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     EdgeSmem& s = *reinterpret_cast<EdgeSmem*>(base);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == MMA_WARP * 32) trace_mark(a.trace, 1, 62, 0);                              // kernel entry
+    if (TRACE && tid == MMA_WARP * 32 && blockIdx.x < 376) {                              // every CTA: global-timer stamp at entry (ns)
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.trace[(64 + 16 + (blockIdx.x >> 3)) * 16 + 2 * (blockIdx.x & 7)] = (long long)gt;
+    }
 
     // The edge count (and, for the round-robin split, the producers' first-tile metadata: loaded speculatively — the
     // arrays hold ecap entries — and masked once E has arrived) is requested before anything else, so that its L2
@@ -145,10 +163,19 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     pdl_launch_dependents();
     pdl_wait();                                       // from here on: data written by earlier kernels of the step
     int s_row = 0, s_col = 0; float s_d0 = 0.f;
+#if EDGE_PREP_WARP
+    int s_row2 = 0, s_col2 = 0; float s_d02 = 0.f;                      // the prep warp: edges lane and lane + 32 of the CTA's first tile
+    if (!a.contig && wid == MMA_WARP + 1) {
+        const int e = (int)blockIdx.x * TILE + lane;
+        if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
+        if (e + 32 < a.ecap) { s_row2 = a.erow[e + 32]; s_col2 = a.ecol[e + 32]; s_d02 = a.d0[e + 32]; }
+    }
+#else
     if (!a.contig && wid >= EPI_WARPS && wid < MMA_WARP && lane < 8) {
         const int e = (int)blockIdx.x * TILE + 8 * (wid - EPI_WARPS) + lane;
         if (e < a.ecap) { s_row = a.erow[e]; s_col = a.ecol[e]; s_d0 = a.d0[e]; }
     }
+#endif
     const int E = *a.n_edges;
 
     // ---- prologue
@@ -157,6 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         mbar_init(smem_u32(&s.bar_wload), 1); mbar_init(smem_u32(&s.bar_wdone), 1);
         for (int i = 0; i < N_XS; ++i) { mbar_init(smem_u32(&s.bar_full[i]), PRO_WARPS); mbar_init(smem_u32(&s.bar_xempty[i]), 1); }
         for (int i = 0; i < N_TS; ++i) { mbar_init(smem_u32(&s.bar_tfull[i]), 1); mbar_init(smem_u32(&s.bar_tempty[i]), EPI_WARPS); }
+        for (int i = 0; i < N_MS; ++i) { mbar_init(smem_u32(&s.bar_mfull[i]), 1); mbar_init(smem_u32(&s.bar_mempty[i]), PRO_WARPS); }
         fence_barrier_init();
     }
     if (wid == MMA_WARP) tmem_alloc(smem_u32(&s.tmem_holder), TMEM_COLS);
@@ -267,6 +295,80 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 if (lane == 0) trace_mark(a.trace, 1, it, 3);
             }
         }
+#if EDGE_PREP_WARP
+        else if (wid == MMA_WARP + 1) {
+            // ================================ metadata prep ================================
+            // Per tile and edge slot j (group j / 16, edge j % 16 of the group's unit): row, col and the two scalar edge
+            // features — d0 from the graph build, r2 recomputed when an endpoint moved (coord2diff, egnn_new.py:265-268) —
+            // as one packed f16x2 word in the packed modes.  One warp does it for all 64 edges (two per lane), up to N_MS
+            // tiles ahead of the producers, instead of each of the 8 producer warps for its own 8 edges on 8 lanes: ~150
+            // index / load instructions per producer warp and tile leave the warps that set the tile period at Calpha size.
+            // Tile my_tiles (no edges: all zero) is produced too, so the producers read "the next tile" unconditionally.
+            float rd_max = 0.f;                                                  // largest r2 / d0 packed to f16 (range guard)
+            // Software pipeline, one L2 round trip per tile in steady state: (row, col, d0) of tile it + 1 are requested
+            // before tile it's coordinates are consumed; the coordinates of moved endpoints go through unconditional loads
+            // of a valid address (no branch), both halves of the tile together.
+            int nr[2], nc[2]; float nd[2];                                       // tile `it`: requested one iteration earlier
+            auto request = [&](int it, int (&r)[2], int (&c)[2], float (&d)[2]) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = lane + 32 * hh, g = j >> 4;
+                    const int e = (unit_base(g) + it * unit_step) * UNIT_TC + (j & 15);
+                    r[hh] = 0; c[hh] = 0; d[hh] = 0.f;
+                    if (it < unit_count(g) && e < E) { r[hh] = a.erow[e]; c[hh] = a.ecol[e]; d[hh] = a.d0[e]; }
+                }
+            };
+            if (a.contig) {
+                request(0, nr, nc, nd);
+            } else {                                                             // requested at kernel entry, masked now that E is known
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = lane + 32 * hh, g = j >> 4;
+                    const bool valid = 0 < unit_count(g) && unit_base(g) * UNIT_TC + (j & 15) < E;
+                    nr[hh] = valid ? (hh ? s_row2 : s_row) : 0; nc[hh] = valid ? (hh ? s_col2 : s_col) : 0; nd[hh] = valid ? (hh ? s_d02 : s_d0) : 0.f;
+                }
+            }
+            for (int it = 0; it <= my_tiles; ++it) {
+                const int ms = it % N_MS;
+                int r[2] = {nr[0], nr[1]}, c[2] = {nc[0], nc[1]};
+                float d0[2] = {nd[0], nd[1]};
+                float xr[2][3], xc[2][3];
+                bool moving[2];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    moving[hh] = r[hh] < a.n_moving || c[hh] < a.n_moving;      // an endpoint moved since the graph build
+                    const int ri = moving[hh] ? 3 * r[hh] : 0, ci = moving[hh] ? 3 * c[hh] : 0;
+                    xr[hh][0] = a.x[ri]; xr[hh][1] = a.x[ri + 1]; xr[hh][2] = a.x[ri + 2];
+                    xc[hh][0] = a.x[ci]; xc[hh][1] = a.x[ci + 1]; xc[hh][2] = a.x[ci + 2];
+                }
+                if (it < my_tiles) request(it + 1, nr, nc, nd);
+                else { nr[0] = nr[1] = nc[0] = nc[1] = 0; nd[0] = nd[1] = 0.f; }
+                if (it >= N_MS) mbar_wait_relaxed(smem_u32(&s.bar_mempty[ms]), ((it / N_MS) & 1) ^ 1);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int j = lane + 32 * hh;
+                    float r2 = d0[hh];
+                    if (moving[hh]) {
+                        const float dx = xr[hh][0] - xc[hh][0], dy = xr[hh][1] - xc[hh][1], dz = xr[hh][2] - xc[hh][2];
+                        r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    }
+                    s.meta[ms].row[j] = r[hh]; s.meta[ms].col[j] = c[hh];
+                    if (PACKED) {
+                        const __half2 t = __floats2half2_rn(fminf(r2, 60000.f), fminf(d0[hh], 60000.f));
+                        s.meta[ms].rd[j] = *reinterpret_cast<const uint32_t*>(&t);
+                        rd_max = fmaxf(rd_max, fmaxf(r2, d0[hh]));
+                    } else {
+                        s.meta[ms].r2[j] = r2; s.meta[ms].d0[j] = d0[hh];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s.bar_mfull[ms]));
+            }
+            // beyond f16's range the clamp makes an edge differ from the reference (only reachable without a cutoff):
+            // flagged once per launch, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
+            if (rd_max > 60000.f) atomicOr(a.range_flag, 2);
+        }
+#endif
     } else if (wid >= EPI_WARPS) {
         // ================================ producer ================================
         // Warp pw owns edges 8 pw .. 8 pw + 7 of every tile; a lane owns 8 channels (128-bit loads / stores).
@@ -281,6 +383,103 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         //     without it (profiles/r04d_producer_dbg.txt).
         //   * (row, col, d0, r2) of the 8 edges live on lanes 0-7, fetched one tile ahead.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_producer(MODE)));
+#if EDGE_PREP_WARP
+        const int pw = wid - EPI_WARPS;
+        float wr[8], wd[8];
+        unpack8(*reinterpret_cast<const float4*>(a.wr + 8 * lane), *reinterpret_cast<const float4*>(a.wr + 8 * lane + 4), wr);
+        unpack8(*reinterpret_cast<const float4*>(a.wd + 8 * lane), *reinterpret_cast<const float4*>(a.wd + 8 * lane + 4), wd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { wr[k] *= 0.5f; wd[k] *= 0.5f; }
+        // packed modes: the same eight halved weights as four f16x2 pairs (the fp32 copies are dead then)
+        __half2 wr2[4], wd2[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            wr2[k2] = __floats2half2_rn(wr[2 * k2], wr[2 * k2 + 1]);
+            wd2[k2] = __floats2half2_rn(wd[2 * k2], wd[2 * k2 + 1]);
+        }
+        const uint32_t ldp_b = 2u * (uint32_t)a.ldp;                                     // row stride in bytes (f16 rows)
+        const __half* pq = reinterpret_cast<const __half*>(a.p);                         // f16 rows, pre-scaled by 1/2 (tc_node.cu)
+        const __half* pa_base = pq + a.off_a + 8 * lane;
+        const __half* pb_base = pq + a.off_b + 8 * lane;
+        // (row, col, packed (r2, d0)) of every tile come from the prep warp through shared memory (broadcast LDS); slots
+        // without an edge hold (0, 0, 0): finite garbage in columns nobody reads.
+        const int e8 = 8 * pw;                                                           // this warp's first edge slot of a tile
+        mbar_wait_relaxed(smem_u32(&s.bar_mfull[0]), 0);
+        uint4 pb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)                                                      // fill the pipeline: the first tile's gathers go out first
+            pb[u] = ldg_na_u4(row_ptr(pb_base, (uint32_t)s.meta[0].col[e8 + u], ldp_b));
+        // Pa of the current CSR row run (8 halves).  It changes once per run; the reload for the NEXT edge's row is issued
+        // before this edge's arithmetic, so an L2 round trip hides behind one edge of work instead of sitting in the chain
+        int cur_row = s.meta[0].row[e8];
+        uint4 cur = ldg_u4(row_ptr(pa_base, (uint32_t)cur_row, ldp_b));
+        unsigned char* const x_gen = s.x[0] + (((lane >> 3) << 13) | (pw << 10));     // K panel of the lane's chunk, row 8 pw
+        const int l74 = (lane & 7) << 4;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const int xs = it % N_XS, cs = it % N_MS, ns = (it + 1) % N_MS;
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 0);
+            mbar_wait_relaxed(smem_u32(&s.bar_mfull[ns]), ((it + 1) / N_MS) & 1);        // the next tile's rows / columns (tile my_tiles: zeros)
+            mbar_wait_relaxed<EDGE_PRODUCER_SLEEP_NS>(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);   // up to 3 tiles ahead: a late wake-up costs nothing
+            if (a.tma_fill && it == 1) mbar_wait_relaxed(smem_u32(&s.bar_wdone), 0);    // stages 1-3 carried the weight panels
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
+            unsigned char* const xt = x_gen + xs * X_TILE_BYTES;
+            const int* const rows_c = s.meta[cs].row + e8;
+            const int* const rows_n = s.meta[ns].row + e8;
+            const int* const cols_n = s.meta[ns].col + e8;
+            // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int next_row = i < 7 ? rows_c[i + 1] : rows_n[0];
+                // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
+                const bool new_run = next_row != cur_row && !(a.dbg & 2);                 // next edge starts a new row run
+                uint4 fresh;                                                             // only read under new_run
+                ldg4_if_noinit(fresh, row_ptr(pa_base, (uint32_t)next_row, ldp_b), new_run);
+                const uint4 nxt = make_uint4(new_run ? fresh.x : cur.x, new_run ? fresh.y : cur.y, new_run ? fresh.z : cur.z, new_run ? fresh.w : cur.w);
+                const uint32_t ca[4] = {cur.x, cur.y, cur.z, cur.w}, cb[4] = {pb[i].x, pb[i].y, pb[i].z, pb[i].w};
+                uint32_t o[4];
+                if (PACKED) {
+                    // two channels per instruction: (Pa' + Pb') + r2 wr' + d0 wd' and SiLU(2 hv) = hv + hv tanh(hv) in
+                    // f16x2; (r2, d0) travel as one packed word, the halves are broadcast by the operand selectors
+                    const uint32_t rd = s.meta[cs].rd[e8 + i];
+                    const __half2 r2h = __low2half2(*reinterpret_cast<const __half2*>(&rd));
+                    const __half2 d0h = __high2half2(*reinterpret_cast<const __half2*>(&rd));
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ca[k2]), *reinterpret_cast<const __half2*>(&cb[k2]));
+                        const __half2 hv = __hfma2(d0h, wd2[k2], __hfma2(r2h, wr2[k2], sum));
+                        __half2 y2;
+                        if (MODE == MODE_F16P) {
+                            y2 = __hfma2(hv, tanh_approx_h2(hv), hv);
+                        } else {
+                            const float2 f = __half22float2(hv);
+                            y2 = __floats2half2_rn(fmaf(f.x, tanh_approx(f.x), f.x), fmaf(f.y, tanh_approx(f.y), f.y));
+                        }
+                        o[k2] = *reinterpret_cast<const uint32_t*>(&y2);
+                    }
+                } else {
+                    const float r2 = s.meta[cs].r2[e8 + i];
+                    const float d0 = s.meta[cs].d0[e8 + i];
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&ca[k2]), *reinterpret_cast<const __half2*>(&cb[k2]));
+                        const float2 f = __half22float2(sum);
+                        o[k2] = pack2<FMT>(silu_half<SFMT>(fmaf(d0, wd[2 * k2], fmaf(r2, wr[2 * k2], f.x))),
+                                           silu_half<SFMT>(fmaf(d0, wd[2 * k2 + 1], fmaf(r2, wr[2 * k2 + 1], f.y))));
+                    }
+                }
+                *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) = make_uint4(o[0], o[1], o[2], o[3]);   // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
+                // refill the slot with the same edge of the next tile
+                pb[i] = ldg_na_u4(row_ptr(pb_base, (uint32_t)cols_n[i], ldp_b));
+                cur = nxt; cur_row = next_row;
+            }
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
+            fence_proxy_async();                                                        // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(smem_u32(&s.bar_full[xs])); mbar_arrive(smem_u32(&s.bar_mempty[cs])); }
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 6);
+        }
+#else
         const int pw = wid - EPI_WARPS;
         const int unit0 = unit_base(pw >> 1), n_units = unit_count(pw >> 1);             // the units of this warp's epilogue group
         const int e_off = 8 * (pw & 1) + lane;                                           // its half of the unit's 16 edges
@@ -350,11 +549,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
             int f_row, f_col; float f_d0;
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 0);
             load_rc(it + 2, f_row, f_col, f_d0);
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 3);
             // next tile: coordinates of moved endpoints (unconditional loads of a valid address, no branch) and L1 touch of its Pa rows
             const bool n_moving = n_row < a.n_moving || n_col < a.n_moving;
             const int xr_i = n_moving ? 3 * n_row : 0, xc_i = n_moving ? 3 * n_col : 0;
             const float xr0 = a.x[xr_i], xr1 = a.x[xr_i + 1], xr2 = a.x[xr_i + 2];
             const float xc0 = a.x[xc_i], xc1 = a.x[xc_i + 1], xc2 = a.x[xc_i + 2];
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 4);
             mbar_wait_relaxed<EDGE_PRODUCER_SLEEP_NS>(smem_u32(&s.bar_xempty[xs]), ((it / N_XS) & 1) ^ 1);   // up to 3 tiles ahead: a late wake-up costs nothing
             if (a.tma_fill && it == 1) mbar_wait_relaxed(smem_u32(&s.bar_wdone), 0);    // stages 1-3 carried the weight panels
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 1);
@@ -365,12 +566,13 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 m_rd = *reinterpret_cast<const uint32_t*>(&t);
                 rd_max = fmaxf(rd_max, fmaxf(m_r2, m_d0));
             }
+            if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 5);
             // one basic block for the 8 edges: no branches, so the scheduler overlaps neighbouring edges
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
 #if EDGE_PA_AHEAD == 2
                 const int row2 = i < 6 ? __shfl_sync(0xffffffffu, m_row, i + 2) : __shfl_sync(0xffffffffu, n_row, i - 6);
-                if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
+                if (TRACE && TRACE_EDGES && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
                 const bool new2 = row2 != row1 && !(a.dbg & 2);
                 uint4 fresh2;                                                            // only read under new2 (as `pend`, two edges on)
                 ldg4_if_noinit(fresh2, row_ptr(pa_base, (uint32_t)row2, ldp_b), new2);
@@ -379,7 +581,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 pend = fresh2; pend_new = new2; row1 = row2;
 #else
                 const int next_row = i < 7 ? __shfl_sync(0xffffffffu, m_row, i + 1) : __shfl_sync(0xffffffffu, n_row, 0);
-                if (TRACE && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
+                if (TRACE && TRACE_EDGES && i < 2 && pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 7 + 4 * i);
                 // loaded into fresh registers and selected afterwards: the reloads of a tile do not depend on each other
                 // (a predicated load straight into a copy of `cur` chains every reload behind the previous one's arrival)
                 const bool new_run = next_row != cur_row && !(a.dbg & 2);                 // next edge starts a new row run
@@ -394,7 +596,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
 #endif
                 const uint4 nxt = make_uint4(new_run ? fresh.x : cur.x, new_run ? fresh.y : cur.y, new_run ? fresh.z : cur.z, new_run ? fresh.w : cur.w);
 #endif
-                if (TRACE && i < 2) {                                                    // timeline only: when Pa / Pb of this edge have landed
+                if (TRACE && TRACE_EDGES && i < 2) {                                     // timeline only: when Pa / Pb of this edge have landed
                     uint32_t t0, t1;
                     asm volatile("mov.b32 %0, %1;" : "=r"(t0) : "r"(cur.x));
                     if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 8 + 4 * i);
@@ -436,7 +638,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
                 *reinterpret_cast<uint4*>(xt + ((i << 7) | (l74 ^ (i << 4)))) = make_uint4(o[0], o[1], o[2], o[3]);   // row 8 pw + i, chunk (lane % 8) ^ (row % 8)
                 // refill the slot with the same edge of the next tile
                 pb[i] = ldg_na_u4(row_ptr(pb_base, (uint32_t)__shfl_sync(0xffffffffu, n_col, i), ldp_b));
-                if (TRACE && i < 2) { asm volatile("" ::: "memory"); if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 10 + 4 * i); }
+                if (TRACE && TRACE_EDGES && i < 2) { asm volatile("" ::: "memory"); if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 10 + 4 * i); }
                 cur = nxt; cur_row = next_row;
             }
             if (pw == 0 && lane == 0) trace_mark(a.trace, 0, it, 2);
@@ -451,6 +653,7 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
         // beyond f16's range the clamp above makes an edge differ from the reference (only reachable without a cutoff):
         // flagged once per launch, the caller re-runs in a mode with fp32 edge features (dp_flags.f16_range)
         if (rd_max > 60000.f) atomicOr(a.range_flag, 2);
+#endif
     } else {
         // ================================ epilogue ================================
         if (regs_epilogue(MODE) > 72) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(regs_epilogue(MODE)));
@@ -635,6 +838,10 @@ __global__ void __launch_bounds__(THREADS, 1) edge_tc_kernel(EdgeArgs a, const u
     __syncthreads();
     if (wid == MMA_WARP) tmem_dealloc(tmem_w, TMEM_COLS);
     if (tid == MMA_WARP * 32) trace_mark(a.trace, 1, 62, 1);                              // kernel exit
+    if (TRACE && tid == MMA_WARP * 32 && blockIdx.x < 376) {                              // ... and at exit
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.trace[(64 + 16 + (blockIdx.x >> 3)) * 16 + 2 * (blockIdx.x & 7) + 1] = (long long)gt;
+    }
 }
 
 }  // namespace

@@ -33,8 +33,20 @@ h.lib.dp_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
 rc = h.lib.dp_debug_trace(h.h, buf, n)
 assert rc == 0, h.lib.dp_last_error()
 tr = [[[buf[(r * 64 + i) * 16 + k] for k in range(16)] for i in range(64)] for r in range(6)]
+# per-CTA global-timer stamps (ns) of the traced launch: MMA role, rows 16.., two words per CTA
+ctas = [(c, tr[1][16 + (c >> 3)][2 * (c & 7)], tr[1][16 + (c >> 3)][2 * (c & 7) + 1]) for c in range(148)]
+ctas = [(c, a, b) for c, a, b in ctas if a and b]
+for r in range(16, 64):
+    tr[1][r] = [0] * 16
+if ctas:
+    g0 = min(a for _, a, _ in ctas)
+    print("per-CTA global timer: launch spans %.2f us (first entry -> last exit); entries within %.2f us; exits %.2f .. %.2f us" % (
+        (max(b for _, _, b in ctas) - g0) / 1e3, (max(a for _, a, _ in ctas) - g0) / 1e3,
+        (min(b for _, _, b in ctas) - g0) / 1e3, (max(b for _, _, b in ctas) - g0) / 1e3))
+    print("  slowest CTAs (cta, entry us, exit us):", [(c, round((a - g0) / 1e3, 2), round((b - g0) / 1e3, 2)) for c, a, b in sorted(ctas, key=lambda t: -t[2])[:8]])
+    print("  fastest CTAs:", [(c, round((a - g0) / 1e3, 2), round((b - g0) / 1e3, 2)) for c, a, b in sorted(ctas, key=lambda t: t[2])[:4]])
 t0 = min(v for r in tr for it in r for v in it if v > 0)
-names = {0: ["start", "xempty", "half", "-", "-", "-", "arrive", "e0 row", "e0 Pa", "e0 Pb", "e0 done", "e1 row", "e1 Pa", "e1 Pb", "e1 done"],
+names = {0: ["start", "xempty", "edges done", "meta issued", "x issued", "block start", "arrive", "e0 row", "e0 Pa", "e0 Pb", "e0 done", "e1 row", "e1 Pa", "e1 Pb", "e1 done"],
          1: ["start", "full", "tempty", "issued"],
          2: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"],
          3: ["start", "tfull", "ld", "silu", "red", "bar", "gate", "seg"]}
