@@ -44,6 +44,11 @@ if ctas:
         (max(b for _, _, b in ctas) - g0) / 1e3, (max(a for _, a, _ in ctas) - g0) / 1e3,
         (min(b for _, _, b in ctas) - g0) / 1e3, (max(b for _, _, b in ctas) - g0) / 1e3))
     print("  slowest CTAs (cta, entry us, exit us):", [(c, round((a - g0) / 1e3, 2), round((b - g0) / 1e3, 2)) for c, a, b in sorted(ctas, key=lambda t: -t[2])[:8]])
+    import statistics
+    for lo, hi in ((0, 37), (37, 55), (55, 83), (83, 148)):
+        grp = [(b - g0) / 1e3 for c, _, b in ctas if lo <= c < hi]
+        if grp:
+            print("  CTAs %3d..%3d: exit median %.2f us (min %.2f, max %.2f)" % (lo, hi - 1, statistics.median(grp), min(grp), max(grp)))
     print("  fastest CTAs:", [(c, round((a - g0) / 1e3, 2), round((b - g0) / 1e3, 2)) for c, a, b in sorted(ctas, key=lambda t: t[2])[:4]])
 t0 = min(v for r in tr for it in r for v in it if v > 0)
 names = {0: ["start", "xempty", "edges done", "meta issued", "x issued", "block start", "arrive", "e0 row", "e0 Pa", "e0 Pb", "e0 done", "e1 row", "e1 Pa", "e1 Pb", "e1 done"],
