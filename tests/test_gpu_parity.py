@@ -606,6 +606,35 @@ def test_graph_replay_equals_eager_launches():
     assert torch.equal(out1, out3)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "f16fast"])
+def test_in_graph_profile_spans(prec):
+    """dp_profile_enable(h, 2): CUDA events recorded as nodes of the captured step graph (read after every replay) time
+    every launch of the production loop; the run's result is the plain run's, the instrumented graph is not kept, and
+    mode 3 (message launch repeated 8x per event pair) leaves the result unchanged too (the kernel is a pure function)."""
+    g = load("sampler_ca_small_T20.npz")
+    cfg = case_config("ca_small")
+    h = make_handle(cfg, int(g["wseed"]), prec)
+    h.plan(g["counts"], g["pocket_size"])
+    tab = step_table(gamma_table("polynomial_2", 20, 1e-5), 20)
+    h.set_step_table(tab.rows, tab.final)
+    xh = torch.cat([T(g["pocket_x"]), T(g["pocket_one_hot"]).float() / 4], 1).to(DEV).contiguous()
+    noise = T(g["noise"]).to(DEV).contiguous()
+    out_plain = h.sample(xh.clone(), noise)
+    caps = h.graph_captures()
+    for mode, calls, reps in ((2, 20, 1), (3, 21, 1)):
+        h.profile_enable(mode)
+        out_prof = h.sample(xh.clone(), noise)
+        spans = [h.profile_read(i) for i in range(6)]
+        h.profile_enable(False)
+        assert torch.equal(out_plain, out_prof)
+        (msg_ms, msg_n), (node_ms, node_n) = spans[0], spans[1]
+        assert msg_n == calls * cfg.n_layers and msg_ms > 0                      # one span per message launch
+        assert spans[2][1] >= calls * cfg.n_layers and spans[4][1] >= calls - 1  # coordinate kernels, DDPM updates
+        assert 1e-3 < msg_ms / msg_n < 5.0                                       # ms per span: sane
+    out_again = h.sample(xh.clone(), noise)                                      # a fresh production graph
+    assert torch.equal(out_plain, out_again) and h.graph_captures() == caps + 2
+
+
 def test_sample_host_equals_device_path():
     g = load("sampler_ca_small_T20.npz")
     cfg = case_config("ca_small")
