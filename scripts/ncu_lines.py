@@ -20,9 +20,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cmd_gen_b200", "libdiffphar_b200.so")
 
 
-def sass_lines(kernel_sub):
+def sass_lines(kernel_sub, want_len=None):
+    """SASS (address, text, source line, inline chain) of the library function whose name contains kernel_sub; with
+    several template instantiations, the one whose instruction count matches the report's (want_len)."""
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, check=True, capture_output=True)
+    found = {}
     for f in sorted(os.listdir(tmp)):
         if not f.endswith(".cubin"):
             continue
@@ -32,7 +35,7 @@ def sass_lines(kernel_sub):
             m = re.match(r"\s*\.text\.(\S+):", ln)
             if m:
                 if res and cur_fn and kernel_sub in cur_fn:
-                    return res
+                    found[cur_fn] = res
                 cur_fn, res, cur_line = m.group(1), [], None
                 continue
             m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
@@ -46,8 +49,14 @@ def sass_lines(kernel_sub):
             if m and cur_fn:
                 res.append((int(m.group(1), 16), m.group(2).strip(), cur_line, inl))
         if res and cur_fn and kernel_sub in cur_fn:
-            return res
-    raise SystemExit(f"kernel {kernel_sub} not found in {LIB}")
+            found[cur_fn] = res
+    if not found:
+        raise SystemExit(f"kernel {kernel_sub} not found in {LIB}")
+    if want_len is None:
+        return next(iter(found.values()))
+    name = min(found, key=lambda k: abs(len(found[k]) - want_len))
+    print(f"# library function: {name} ({len(found[name])} instructions)")
+    return found[name]
 
 
 def main():
@@ -66,7 +75,7 @@ def main():
     ci = {h: i for i, h in enumerate(hdr)}
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     data = rows[hi + 1:]
-    sass = sass_lines(ksub)
+    sass = sass_lines(ksub, len(data))
     if len(sass) != len(data):
         print(f"# warning: {len(data)} instructions in the report vs {len(sass)} in the library (rebuilt since?)")
     agg = collections.defaultdict(lambda: [0, 0, collections.Counter(), 0])
